@@ -1,0 +1,49 @@
+"""Shared helpers for the parity tests: seeded small scenes + oracle/dense invocation."""
+from __future__ import annotations
+
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from humangaussian_b200.cameras import Camera, orbit_c2w  # noqa: E402
+from humangaussian_b200.scene import synthetic_body  # noqa: E402
+
+
+def small_scene(P=200, deg=1, seed=0, H=40, W=56, elev=12.0, azim=35.0, dist=1.6, fovy_deg=55.0, big=True):
+    """Activated inputs (numpy float32) + camera for one view of a synthetic body."""
+    p = synthetic_body(P, sh_degree=deg, seed=seed)
+    if big:  # enlarge so that a few hundred Gaussians cover a tiny image with real overlap
+        p.scaling += math.log(6.0)
+        p.opacity += 1.5
+    cam = Camera(orbit_c2w(elev, azim, dist), math.radians(fovy_deg), H, W)
+    with torch.no_grad():
+        inp = dict(
+            means3D=p.get_xyz.numpy().copy(), opacities=p.get_opacity.numpy().copy(),
+            shs=p.get_features.numpy().copy(), scales=p.get_scaling.numpy().copy(),
+            rotations=p.get_rotation.numpy().copy(), sh_degree=deg,
+            viewmatrix=cam.world_view_transform.numpy().copy(), projmatrix=cam.full_proj_transform.numpy().copy(),
+            campos=cam.camera_center.numpy().copy(), bg=np.array([0.1, 0.4, 0.7], np.float32),
+            image_height=H, image_width=W, tanfovx=math.tan(cam.FoVx * 0.5), tanfovy=math.tan(cam.FoVy * 0.5),
+            scale_modifier=1.0)
+    return inp, cam, p
+
+
+def grad_images(H, W, seed=0):
+    rng = np.random.RandomState(seed)
+    return (rng.randn(3, H, W).astype(np.float32), rng.randn(1, H, W).astype(np.float32),
+            rng.randn(1, H, W).astype(np.float32))
+
+
+def close(a, b, atol=1e-5, rtol=1e-4):
+    """The north-star tolerance: |a-b| <= 1e-5 + 1e-4*|b|.  Returns (ok, worst violation ratio)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    err = np.abs(a - b)
+    lim = atol + rtol * np.abs(b)
+    return bool((err <= lim).all()), float((err / lim).max()) if err.size else 0.0
