@@ -1,0 +1,212 @@
+// api.cu -- the C-ABI of libb200gs (include/b200gs.h): argument validation, state-buffer carving,
+// kernel sequencing.  No torch types, no global state except an error string and a launch counter.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/b200gs.h"
+#include "common.cuh"
+#include "kernels.h"
+
+static thread_local char g_err[256] = "";
+static std::atomic<int64_t> g_launches{0};
+
+static int cuda_fail(cudaError_t e, const char *where)
+{
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return B200GS_E_CUDA;
+}
+#define CK(call, where)                                  \
+    do {                                                 \
+        cudaError_t e__ = (call);                        \
+        if (e__ != cudaSuccess) return cuda_fail(e__, where); \
+    } while (0)
+
+extern "C" {
+
+const char *b200gs_last_cuda_error(void) { return g_err; }
+int b200gs_abi_version(void) { return B200GS_ABI_VERSION; }
+int64_t b200gs_launch_count(void) { return g_launches.load(); }
+
+size_t b200gs_geom_bytes(int32_t P, int32_t V) { return GeomLayout(P, V).total; }
+size_t b200gs_image_bytes(int32_t H, int32_t W, int32_t V) { return ImageLayout(H, W, V).total; }
+size_t b200gs_binning_bytes(int64_t cap, int32_t H, int32_t W, int32_t P, int32_t V)
+{
+    const int gx = (W + GS_TILE - 1) / GS_TILE, gy = (H + GS_TILE - 1) / GS_TILE;
+    return binning_layout(cap, gx * gy * V, (int64_t)P * V).total;
+}
+size_t b200gs_backward_scratch_bytes(int32_t P, int32_t V) { return gs_align((size_t)P * V * sizeof(ScreenGrad)); }
+
+static int check_common(const b200gs_params *p, const float *shs, const float *colors, const float *scales,
+                        const float *rots, const float *cov)
+{
+    if (!p || p->abi_version != B200GS_ABI_VERSION) return B200GS_E_ARGS;
+    if (p->P < 0 || p->n_views < 1 || p->image_height < 1 || p->image_width < 1 || !p->tanfovx || !p->tanfovy) return B200GS_E_ARGS;
+    if ((shs == nullptr) == (colors == nullptr)) return B200GS_E_ARGS;
+    if (((scales == nullptr) || (rots == nullptr)) == (cov == nullptr)) return B200GS_E_ARGS;
+    if ((scales == nullptr) != (rots == nullptr)) return B200GS_E_ARGS;
+    if (p->n_views > B200GS_MAX_VIEWS) return B200GS_E_RANGE;
+    if (shs && (p->sh_degree < 0 || p->sh_degree > 3 || p->sh_coeffs < (p->sh_degree + 1) * (p->sh_degree + 1))) return B200GS_E_RANGE;
+    if ((int64_t)p->P * p->n_views >= ((int64_t)1 << 32)) return B200GS_E_RANGE;
+    if ((p->image_width + GS_TILE - 1) / GS_TILE > 65535 || (p->image_height + GS_TILE - 1) / GS_TILE > 65535) return B200GS_E_RANGE;
+    return B200GS_OK;
+}
+
+int b200gs_forward(const b200gs_params *prm, const float *means3D, const float *shs, const float *colors_precomp,
+                   const float *opacities, const float *scales, const float *rotations, const float *cov3D_precomp,
+                   const float *bg, const float *viewmatrix, const float *projmatrix, const float *campos,
+                   float *out_color, float *out_depth, float *out_alpha, int32_t *radii, void *geom_buf, size_t geom_bytes,
+                   void *binning_buf, size_t binning_bytes, int64_t instance_capacity, void *image_buf, size_t image_bytes,
+                   int64_t *num_rendered, void *stream)
+{
+    int rc = check_common(prm, shs, colors_precomp, scales, rotations, cov3D_precomp);
+    if (rc) return rc;
+    if (!means3D || !opacities || !bg || !viewmatrix || !projmatrix || !campos || !out_color || !out_depth || !out_alpha ||
+        !radii || !geom_buf || !binning_buf || !image_buf || !num_rendered)
+        return B200GS_E_ARGS;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int P = prm->P, V = prm->n_views, H = prm->image_height, W = prm->image_width;
+    const int gx = (W + GS_TILE - 1) / GS_TILE, gy = (H + GS_TILE - 1) / GS_TILE;
+    const GeomLayout GL(P, V);
+    const ImageLayout IL(H, W, V);
+    const BinLayout BL = binning_layout(instance_capacity, gx * gy * V, (int64_t)P * V);
+    if (geom_bytes < GL.total || image_bytes < IL.total || binning_bytes < BL.total) return B200GS_E_BUFFER;
+    char *gb = (char *)geom_buf, *bb = (char *)binning_buf, *ib = (char *)image_buf;
+    const size_t HW = (size_t)H * W;
+    *num_rendered = 0;
+
+    if (P == 0) { // empty scene: background only
+        CK(cudaMemsetAsync(bb + BL.ranges, 0, (size_t)gx * gy * V * 8, st), "memset ranges");
+    } else {
+        PreArgs a;
+        a.P = P; a.deg = shs ? prm->sh_degree : 0; a.M = prm->sh_coeffs; a.H = H; a.W = W; a.grid_x = gx; a.grid_y = gy;
+        a.mod = prm->scale_modifier;
+        a.means = means3D; a.shs = shs; a.colors_pre = colors_precomp; a.opac = opacities; a.scales = scales;
+        a.rots = rotations; a.cov_pre = cov3D_precomp; a.view = viewmatrix; a.proj = projmatrix; a.campos = campos;
+        for (int v = 0; v < V; v++) { a.tanfovx[v] = prm->tanfovx[v]; a.tanfovy[v] = prm->tanfovy[v]; }
+        a.radii = radii; a.recs = (GeomRec *)(gb + GL.recs); a.tiles_touched = (uint32_t *)(gb + GL.tiles_touched);
+        a.rects = (uint2 *)(gb + GL.rects); a.clamped = (uint8_t *)(gb + GL.clamped);
+        launch_preprocess_fwd(a, V, st);
+        g_launches += 1;
+        uint32_t *offsets = (uint32_t *)(gb + GL.offsets);
+        const int64_t n_vp = (int64_t)P * V;
+        if (launch_scan_tiles(a.tiles_touched, offsets, n_vp, bb + BL.temp, BL.temp_bytes, st)) return cuda_fail(cudaGetLastError(), "scan");
+        g_launches += 2;
+        uint32_t total = 0;
+        CK(cudaMemcpyAsync(&total, offsets + (n_vp - 1), 4, cudaMemcpyDeviceToHost, st), "D2H num_rendered");
+        CK(cudaStreamSynchronize(st), "sync after scan");
+        *num_rendered = (int64_t)total;
+        if ((int64_t)total > instance_capacity) return B200GS_E_BIN_TOO_SMALL;
+        int nl = 0;
+        if (launch_binning(a.recs, a.rects, offsets, P, V, gx, gy, (int64_t)total, bb, BL, st, &nl)) return cuda_fail(cudaGetLastError(), "binning");
+        g_launches += nl + (total ? 4 : 0);
+    }
+    BlendArgs b;
+    b.H = H; b.W = W; b.grid_x = gx; b.grid_y = gy; b.V = V; b.P = P;
+    b.ranges = (const uint2 *)(bb + BL.ranges); b.point_list = (const uint32_t *)(bb + BL.vals_out);
+    b.recs = (const GeomRec *)(gb + GL.recs); b.bg = bg;
+    b.final_T = (float *)(ib + IL.final_T); b.n_contrib = (uint32_t *)(ib + IL.n_contrib);
+    b.out_color = out_color; b.out_depth = out_depth; b.out_alpha = out_alpha;
+    (void)HW;
+    launch_blend_fwd(b, st);
+    g_launches += 1;
+    CK(cudaGetLastError(), "forward launch");
+    return B200GS_OK;
+}
+
+int b200gs_backward(const b200gs_params *prm, const float *means3D, const float *shs, const float *colors_precomp,
+                    const float *opacities, const float *scales, const float *rotations, const float *cov3D_precomp,
+                    const float *bg, const float *viewmatrix, const float *projmatrix, const float *campos,
+                    const int32_t *radii, const void *geom_buf, const void *binning_buf, int64_t instance_capacity,
+                    const void *image_buf, int64_t num_rendered, const float *dL_dcolor, const float *dL_ddepth,
+                    const float *dL_dalpha, float *dL_dmeans3D, float *dL_dmeans2D, float *dL_dsh, float *dL_dcolors,
+                    float *dL_dopacity, float *dL_dscales, float *dL_drots, float *dL_dcov3D, void *scratch,
+                    size_t scratch_bytes, void *stream)
+{
+    (void)opacities; (void)num_rendered;
+    int rc = check_common(prm, shs, colors_precomp, scales, rotations, cov3D_precomp);
+    if (rc) return rc;
+    if (!means3D || !bg || !viewmatrix || !projmatrix || !campos || !radii || !geom_buf || !binning_buf || !image_buf ||
+        !dL_dmeans3D || !dL_dmeans2D || !dL_dopacity || !scratch)
+        return B200GS_E_ARGS;
+    if (shs ? !dL_dsh : !dL_dcolors) return B200GS_E_ARGS;
+    if (scales ? (!dL_dscales || !dL_drots) : !dL_dcov3D) return B200GS_E_ARGS;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int P = prm->P, V = prm->n_views, H = prm->image_height, W = prm->image_width;
+    if (P == 0) return B200GS_OK;
+    const int gx = (W + GS_TILE - 1) / GS_TILE, gy = (H + GS_TILE - 1) / GS_TILE;
+    const GeomLayout GL(P, V);
+    const ImageLayout IL(H, W, V);
+    const BinLayout BL = binning_layout(instance_capacity, gx * gy * V, (int64_t)P * V);
+    if (scratch_bytes < b200gs_backward_scratch_bytes(P, V)) return B200GS_E_BUFFER;
+    const char *gb = (const char *)geom_buf, *bb = (const char *)binning_buf, *ib = (const char *)image_buf;
+
+    CK(cudaMemsetAsync(scratch, 0, (size_t)P * V * sizeof(ScreenGrad), st), "memset scratch");
+    BlendBwdArgs b;
+    b.H = H; b.W = W; b.grid_x = gx; b.grid_y = gy; b.V = V; b.P = P;
+    b.ranges = (const uint2 *)(bb + BL.ranges); b.point_list = (const uint32_t *)(bb + BL.vals_out);
+    b.recs = (const GeomRec *)(gb + GL.recs); b.bg = bg;
+    b.final_T = (const float *)(ib + IL.final_T); b.n_contrib = (const uint32_t *)(ib + IL.n_contrib);
+    b.dL_dcolor = dL_dcolor; b.dL_ddepth = dL_ddepth; b.dL_dalpha = dL_dalpha;
+    b.sgrad = (ScreenGrad *)scratch;
+    launch_blend_bwd(b, st);
+
+    PreBwdArgs a;
+    a.P = P; a.V = V; a.deg = shs ? prm->sh_degree : 0; a.M = prm->sh_coeffs; a.H = H; a.W = W; a.mod = prm->scale_modifier;
+    a.means = means3D; a.shs = shs; a.colors_pre = colors_precomp; a.scales = scales; a.rots = rotations; a.cov_pre = cov3D_precomp;
+    a.view = viewmatrix; a.proj = projmatrix; a.campos = campos;
+    for (int v = 0; v < V; v++) { a.tanfovx[v] = prm->tanfovx[v]; a.tanfovy[v] = prm->tanfovy[v]; }
+    a.radii = radii; a.clamped = (const uint8_t *)(gb + GL.clamped); a.sgrad = (const ScreenGrad *)scratch;
+    a.dL_dmeans3D = dL_dmeans3D; a.dL_dmeans2D = dL_dmeans2D; a.dL_dsh = dL_dsh; a.dL_dcolors = dL_dcolors;
+    a.dL_dopacity = dL_dopacity; a.dL_dscales = dL_dscales; a.dL_drots = dL_drots; a.dL_dcov3D = dL_dcov3D;
+    launch_preprocess_bwd(a, st);
+    g_launches += 2;
+    CK(cudaGetLastError(), "backward launch");
+    return B200GS_OK;
+}
+
+int b200gs_mark_visible(int32_t P, const float *positions, const float *viewmatrix, const float *projmatrix,
+                        uint8_t *present, void *stream)
+{
+    (void)projmatrix;
+    if (P < 0 || !positions || !viewmatrix || !present) return B200GS_E_ARGS;
+    if (P == 0) return B200GS_OK;
+    launch_mark_visible(P, positions, viewmatrix, present, (cudaStream_t)stream);
+    g_launches += 1;
+    CK(cudaGetLastError(), "mark_visible launch");
+    return B200GS_OK;
+}
+
+int b200gs_describe_state(const b200gs_params *prm, const void *geom_buf, const void *binning_buf, int64_t instance_capacity,
+                          const void *image_buf, b200gs_state_view *out)
+{
+    if (!prm || !out || !geom_buf || !binning_buf || !image_buf) return B200GS_E_ARGS;
+    const int P = prm->P, V = prm->n_views, H = prm->image_height, W = prm->image_width;
+    const int gx = (W + GS_TILE - 1) / GS_TILE, gy = (H + GS_TILE - 1) / GS_TILE;
+    const GeomLayout GL(P, V);
+    const ImageLayout IL(H, W, V);
+    const BinLayout BL = binning_layout(instance_capacity, gx * gy * V, (int64_t)P * V);
+    const char *gb = (const char *)geom_buf, *bb = (const char *)binning_buf, *ib = (const char *)image_buf;
+    out->geom_records = gb + GL.recs;
+    out->tiles_touched = (const uint32_t *)(gb + GL.tiles_touched);
+    out->offsets = (const uint32_t *)(gb + GL.offsets);
+    out->clamped = (const uint8_t *)(gb + GL.clamped);
+    out->sorted_keys = (const uint64_t *)(bb + BL.keys_out);
+    out->point_list = (const uint32_t *)(bb + BL.vals_out);
+    out->ranges = (const uint32_t *)(bb + BL.ranges);
+    out->final_T = (const float *)(ib + IL.final_T);
+    out->n_contrib = (const uint32_t *)(ib + IL.n_contrib);
+    return B200GS_OK;
+}
+
+int b200gs_test_exp(const float *x, float *y, int64_t n, void *stream)
+{
+    if (n < 0 || !x || !y) return B200GS_E_ARGS;
+    if (n == 0) return B200GS_OK;
+    launch_test_exp(x, y, n, (cudaStream_t)stream);
+    g_launches += 1;
+    CK(cudaGetLastError(), "test_exp launch");
+    return B200GS_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,70 @@
+// kernels.h -- argument blocks and launchers shared by the translation units of libb200gs.
+#pragma once
+#include "common.cuh"
+
+struct PreArgs {
+    int P, deg, M, H, W, grid_x, grid_y;
+    float mod;
+    const float *means, *shs, *colors_pre, *opac, *scales, *rots, *cov_pre;
+    const float *view, *proj, *campos; // [V,16] [V,16] [V,3]
+    float tanfovx[GS_MAX_VIEWS], tanfovy[GS_MAX_VIEWS];
+    // outputs
+    int32_t *radii;          // [V,P]
+    GeomRec *recs;           // [V*P]
+    uint32_t *tiles_touched; // [V*P]
+    uint2 *rects;            // [V*P]
+    uint8_t *clamped;        // [V*P]
+};
+
+struct PreBwdArgs {
+    int P, V, deg, M, H, W;
+    float mod;
+    const float *means, *shs, *colors_pre, *scales, *rots, *cov_pre;
+    const float *view, *proj, *campos;
+    float tanfovx[GS_MAX_VIEWS], tanfovy[GS_MAX_VIEWS];
+    const int32_t *radii;
+    const uint8_t *clamped;
+    const ScreenGrad *sgrad; // [V*P]
+    float *dL_dmeans3D, *dL_dmeans2D, *dL_dsh, *dL_dcolors, *dL_dopacity, *dL_dscales, *dL_drots, *dL_dcov3D;
+};
+
+struct BlendArgs {
+    int H, W, grid_x, grid_y, V, P;
+    const uint2 *ranges;        // [V*tiles]
+    const uint32_t *point_list; // [D] index into recs (= v*P + gaussian)
+    const GeomRec *recs;        // [V*P]
+    const float *bg;            // [3]
+    float *final_T;             // [V,H,W]
+    uint32_t *n_contrib;        // [V,H,W]
+    float *out_color, *out_depth, *out_alpha;
+};
+
+struct BlendBwdArgs {
+    int H, W, grid_x, grid_y, V, P;
+    const uint2 *ranges;
+    const uint32_t *point_list;
+    const GeomRec *recs;
+    const float *bg;
+    const float *final_T;
+    const uint32_t *n_contrib;
+    const float *dL_dcolor, *dL_ddepth, *dL_dalpha; // may be null
+    ScreenGrad *sgrad;                              // [V*P], zeroed by the caller
+};
+
+void launch_preprocess_fwd(const PreArgs &a, int V, cudaStream_t st);
+void launch_preprocess_bwd(const PreBwdArgs &a, cudaStream_t st);
+void launch_mark_visible(int P, const float *pos, const float *V, uint8_t *present, cudaStream_t st);
+
+// binning: inclusive scan, key emission, sort, tile ranges
+struct BinLayout {
+    size_t keys_in, keys_out, vals_in, vals_out, ranges, temp, total;
+    size_t temp_bytes;
+};
+BinLayout binning_layout(int64_t capacity, int ntiles_total, int64_t n_vp);
+int launch_scan_tiles(const uint32_t *tiles_touched, uint32_t *offsets, int64_t n, void *temp, size_t temp_bytes, cudaStream_t st);
+int launch_binning(const GeomRec *recs, const uint2 *rects, const uint32_t *offsets, int P, int V, int grid_x, int grid_y,
+                   int64_t D, char *bin_base, const BinLayout &L, cudaStream_t st, int *n_launches);
+
+void launch_blend_fwd(const BlendArgs &a, cudaStream_t st);
+void launch_blend_bwd(const BlendBwdArgs &a, cudaStream_t st);
+void launch_test_exp(const float *x, float *y, int64_t n, cudaStream_t st);

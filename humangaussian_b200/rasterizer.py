@@ -1,0 +1,362 @@
+"""Host side of the drop-in boundary: the `diff_gaussian_rasterization` surface over the C-ABI.
+
+Mirrors the un-vendored package HumanGaussian imports (same names, argument meaning, error behaviour):
+  * ``GaussianRasterizationSettings`` -- 12-field NamedTuple built at
+    gaussiansplatting/gaussian_renderer/__init__.py:36-49 and gs_renderer.py:951-964;
+  * ``GaussianRasterizer(raster_settings=...)`` -- nn.Module called with keywords
+    (gaussian_renderer/__init__.py:86-94, gs_renderer.py:1006-1015) returning
+    ``(color[3,H,W], radii[P] int32, depth[1,H,W], alpha[1,H,W])``, differentiable w.r.t.
+    means3D, means2D (gradient sink), shs | colors_precomp, opacities, scales+rotations | cov3D_precomp.
+Plus the view-batched entry ``rasterize_views`` (one call for the V cameras of an SDS batch,
+threestudio/systems/GaussianDreamer.py:244-248).
+
+Everything numerical happens in libb200gs.so (hand-written sm_100a CUDA behind include/b200gs.h),
+reached through ctypes with raw device pointers.  There is NO CPU or PyTorch fallback: if the
+library is missing or the tensors are not on a CUDA device this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import NamedTuple, Optional
+
+import torch
+from torch import nn
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200gs.so")
+ABI_VERSION = 1
+MAX_VIEWS = 64
+
+OK, E_ARGS, E_BIN_TOO_SMALL, E_BUFFER, E_CUDA, E_RANGE = 0, -1, -2, -3, -4, -5
+
+
+class _Params(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("P", C.c_int32), ("n_views", C.c_int32), ("sh_degree", C.c_int32),
+                ("sh_coeffs", C.c_int32), ("image_height", C.c_int32), ("image_width", C.c_int32),
+                ("prefiltered", C.c_int32), ("debug", C.c_int32), ("scale_modifier", C.c_float),
+                ("tanfovx", C.POINTER(C.c_float)), ("tanfovy", C.POINTER(C.c_float))]
+
+
+class _StateView(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("geom_records", "tiles_touched", "offsets", "clamped", "sorted_keys",
+                                          "point_list", "ranges", "final_T", "n_contrib")]
+
+
+_lib = None
+EXPORTS = ["b200gs_forward", "b200gs_backward", "b200gs_mark_visible", "b200gs_describe_state", "b200gs_test_exp",
+           "b200gs_geom_bytes", "b200gs_image_bytes", "b200gs_binning_bytes", "b200gs_backward_scratch_bytes",
+           "b200gs_last_cuda_error", "b200gs_abi_version", "b200gs_launch_count"]
+
+
+def load_library():
+    """dlopen libb200gs.so and declare signatures.  Raises (never falls back) if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"b200gs: {LIB_PATH} not built -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a).  There is no CPU/PyTorch fallback for the rasteriser.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+    L.b200gs_abi_version.restype = C.c_int
+    if L.b200gs_abi_version() != ABI_VERSION:
+        raise RuntimeError("b200gs: ABI version mismatch between rasterizer.py and libb200gs.so")
+    L.b200gs_geom_bytes.restype = sz; L.b200gs_geom_bytes.argtypes = [i32, i32]
+    L.b200gs_image_bytes.restype = sz; L.b200gs_image_bytes.argtypes = [i32, i32, i32]
+    L.b200gs_binning_bytes.restype = sz; L.b200gs_binning_bytes.argtypes = [i64, i32, i32, i32, i32]
+    L.b200gs_backward_scratch_bytes.restype = sz; L.b200gs_backward_scratch_bytes.argtypes = [i32, i32]
+    L.b200gs_forward.restype = C.c_int
+    L.b200gs_forward.argtypes = [C.POINTER(_Params)] + [vp] * 15 + [vp, sz, vp, sz, i64, vp, sz, C.POINTER(i64), vp]
+    L.b200gs_backward.restype = C.c_int
+    L.b200gs_backward.argtypes = [C.POINTER(_Params)] + [vp] * 12 + [vp, vp, i64, vp, i64] + [vp] * 11 + [vp, sz, vp]
+    L.b200gs_mark_visible.restype = C.c_int
+    L.b200gs_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
+    L.b200gs_describe_state.restype = C.c_int
+    L.b200gs_describe_state.argtypes = [C.POINTER(_Params), vp, vp, i64, vp, C.POINTER(_StateView)]
+    L.b200gs_test_exp.restype = C.c_int
+    L.b200gs_test_exp.argtypes = [vp, vp, i64, vp]
+    L.b200gs_last_cuda_error.restype = C.c_char_p
+    L.b200gs_launch_count.restype = i64
+    _lib = L
+    return L
+
+
+def launch_count() -> int:
+    return int(load_library().b200gs_launch_count())
+
+
+def _check(rc, what):
+    if rc == OK:
+        return
+    L = load_library()
+    msg = {E_ARGS: "inconsistent arguments", E_BUFFER: "state buffer too small", E_RANGE: "size outside supported range",
+           E_CUDA: "CUDA error: " + (L.b200gs_last_cuda_error() or b"").decode()}.get(rc, f"status {rc}")
+    raise RuntimeError(f"b200gs {what} failed: {msg}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32c(t: Optional[torch.Tensor], device=None):
+    if t is None:
+        return None
+    if device is not None and t.device != device:
+        t = t.to(device)
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+# instance-capacity hint per (device, P, V, H, W): avoids the retry after the first call
+_cap_hint: dict = {}
+
+
+class _Ctx:
+    """What one forward keeps for its backward (upstream keeps geomBuffer/binningBuffer/imgBuffer the same way)."""
+    __slots__ = ("prm", "tanx", "tany", "geom", "binning", "image", "capacity", "num_rendered", "radii", "V", "P", "H", "W", "M")
+
+
+def _make_params(P, V, deg, M, H, W, mod, tanx, tany, prefiltered=False, debug=False):
+    tx = (C.c_float * V)(*[float(t) for t in tanx])
+    ty = (C.c_float * V)(*[float(t) for t in tany])
+    prm = _Params(ABI_VERSION, P, V, int(deg), int(M), int(H), int(W), int(bool(prefiltered)), int(bool(debug)), float(mod),
+                  C.cast(tx, C.POINTER(C.c_float)), C.cast(ty, C.POINTER(C.c_float)))
+    return prm, tx, ty
+
+
+def _forward_impl(means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, viewmatrix, projmatrix,
+                  campos, tanfovx, tanfovy, H, W, sh_degree, scale_modifier, prefiltered=False, debug=False):
+    """All tensors float32 contiguous on one CUDA device.  viewmatrix/projmatrix [V,4,4], campos [V,3]."""
+    L = load_library()
+    dev = means3D.device
+    if dev.type != "cuda":
+        raise RuntimeError("b200gs: tensors must live on a CUDA device (there is no CPU path)")
+    P, V = means3D.shape[0], viewmatrix.shape[0]
+    if (shs is None) == (colors_precomp is None):
+        raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+    if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+            ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+        raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+    M = 0 if shs is None else shs.shape[1]
+    prm, tx, ty = _make_params(P, V, sh_degree, M, H, W, scale_modifier, tanfovx, tanfovy, prefiltered, debug)
+    u8 = dict(dtype=torch.uint8, device=dev)
+    geom = torch.empty(L.b200gs_geom_bytes(P, V), **u8)
+    image = torch.empty(L.b200gs_image_bytes(H, W, V), **u8)
+    color = torch.empty(V, 3, H, W, dtype=torch.float32, device=dev)
+    depth = torch.empty(V, 1, H, W, dtype=torch.float32, device=dev)
+    alpha = torch.empty(V, 1, H, W, dtype=torch.float32, device=dev)
+    radii = torch.empty(V, P, dtype=torch.int32, device=dev)
+    key = (dev.index, P, V, H, W)
+    cap = _cap_hint.get(key, max(1 << 16, 4 * P * V))
+    n_out = C.c_int64(0)
+    with torch.cuda.device(dev):
+        for _ in range(3):
+            binning = torch.empty(L.b200gs_binning_bytes(cap, H, W, P, V), **u8)
+            rc = L.b200gs_forward(C.byref(prm), _ptr(means3D), _ptr(shs), _ptr(colors_precomp), _ptr(opacities), _ptr(scales),
+                                  _ptr(rotations), _ptr(cov3D_precomp), _ptr(bg), _ptr(viewmatrix), _ptr(projmatrix),
+                                  _ptr(campos), _ptr(color), _ptr(depth), _ptr(alpha), _ptr(radii), _ptr(geom), geom.numel(),
+                                  _ptr(binning), binning.numel(), cap, _ptr(image), image.numel(), C.byref(n_out), _stream(dev))
+            if rc != E_BIN_TOO_SMALL:
+                break
+            cap = int(n_out.value * 1.25) + 1024
+        _check(rc, "forward")
+    _cap_hint[key] = max(int(n_out.value * 1.25) + 1024, 1 << 16)
+    st = _Ctx()
+    st.prm, st.tanx, st.tany = prm, tx, ty
+    st.geom, st.binning, st.image, st.capacity, st.num_rendered = geom, binning, image, cap, int(n_out.value)
+    st.radii, st.V, st.P, st.H, st.W, st.M = radii, V, P, H, W, M
+    return color, radii, depth, alpha, st
+
+
+def _backward_impl(st: _Ctx, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, viewmatrix,
+                   projmatrix, campos, g_color, g_depth, g_alpha):
+    L = load_library()
+    dev = means3D.device
+    P, V, M = st.P, st.V, st.M
+    f = dict(dtype=torch.float32, device=dev)
+    d_means3D = torch.empty(P, 3, **f)
+    d_means2D = torch.empty(V, P, 3, **f)
+    d_op = torch.empty(P, 1, **f)
+    d_sh = torch.empty(P, M, 3, **f) if shs is not None else None
+    d_col = torch.empty(P, 3, **f) if colors_precomp is not None else None
+    d_sc = torch.empty(P, 3, **f) if scales is not None else None
+    d_rot = torch.empty(P, 4, **f) if rotations is not None else None
+    d_cov = torch.empty(P, 6, **f) if cov3D_precomp is not None else None
+    if P == 0:
+        return d_means3D, d_means2D, d_sh, d_col, d_op, d_sc, d_rot, d_cov
+    scratch = torch.empty(L.b200gs_backward_scratch_bytes(P, V), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.b200gs_backward(C.byref(st.prm), _ptr(means3D), _ptr(shs), _ptr(colors_precomp), _ptr(opacities), _ptr(scales),
+                               _ptr(rotations), _ptr(cov3D_precomp), _ptr(bg), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos),
+                               _ptr(st.radii), _ptr(st.geom), _ptr(st.binning), st.capacity, _ptr(st.image), st.num_rendered,
+                               _ptr(g_color), _ptr(g_depth), _ptr(g_alpha), _ptr(d_means3D), _ptr(d_means2D), _ptr(d_sh),
+                               _ptr(d_col), _ptr(d_op), _ptr(d_sc), _ptr(d_rot), _ptr(d_cov), _ptr(scratch), scratch.numel(),
+                               _stream(dev))
+    _check(rc, "backward")
+    return d_means3D, d_means2D, d_sh, d_col, d_op, d_sc, d_rot, d_cov
+
+
+class _RasterizeViews(torch.autograd.Function):
+    """V >= 1 views of one Gaussian set.  means2D is [V,P,3] (or [P,3] when V == 1 and squeeze=True)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, cams, squeeze):
+        bg, viewmatrix, projmatrix, campos, tanx, tany, H, W, deg, mod, prefiltered, debug = cams
+        dev = means3D.device
+        args = [_f32c(t, dev) for t in (means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp)]
+        camt = [_f32c(t, dev) for t in (bg, viewmatrix, projmatrix, campos)]
+        color, radii, depth, alpha, st = _forward_impl(*args, *camt, tanx, tany, H, W, deg, mod, prefiltered, debug)
+        ctx.st, ctx.squeeze = st, squeeze
+        ctx.saved = args + camt  # plain references: these are detached copies or the caller's own storage
+        ctx.mark_non_differentiable(radii)
+        if squeeze:
+            return color[0], radii[0], depth[0], alpha[0]
+        return color, radii, depth, alpha
+
+    @staticmethod
+    def backward(ctx, g_color, g_radii, g_depth, g_alpha):
+        st = ctx.st
+        means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, viewmatrix, projmatrix, campos = ctx.saved
+        dev = means3D.device
+        g = [None if t is None else _f32c(t, dev) for t in (g_color, g_depth, g_alpha)]
+        d_means3D, d_means2D, d_sh, d_col, d_op, d_sc, d_rot, d_cov = _backward_impl(
+            st, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, viewmatrix, projmatrix, campos, *g)
+        if ctx.squeeze:
+            d_means2D = d_means2D[0]
+        ctx.st = None
+        ctx.saved = None
+        return d_means3D, d_means2D, d_sh, d_col, d_op, d_sc, d_rot, d_cov, None, None
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+def _cams_from_settings(s: GaussianRasterizationSettings):
+    return (s.bg, s.viewmatrix.reshape(1, 4, 4), s.projmatrix.reshape(1, 4, 4), s.campos.reshape(1, 3), [s.tanfovx], [s.tanfovy],
+            int(s.image_height), int(s.image_width), int(s.sh_degree), float(s.scale_modifier), s.prefiltered, s.debug)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+    empty = lambda t: None if (t is None or t.numel() == 0) else t
+    return _RasterizeViews.apply(means3D, means2D, empty(sh), empty(colors_precomp), opacities, empty(scales), empty(rotations),
+                                 empty(cov3Ds_precomp), _cams_from_settings(raster_settings), True)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        L = load_library()
+        s = self.raster_settings
+        with torch.no_grad():
+            pos = _f32c(positions)
+            present = torch.empty(pos.shape[0], dtype=torch.uint8, device=pos.device)
+            with torch.cuda.device(pos.device):
+                rc = L.b200gs_mark_visible(pos.shape[0], _ptr(pos), _ptr(_f32c(s.viewmatrix, pos.device)),
+                                           _ptr(_f32c(s.projmatrix, pos.device)), _ptr(present), _stream(pos.device))
+            _check(rc, "mark_visible")
+        return present.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None):
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                   self.raster_settings)
+
+
+def rasterize_views(*, means3D, opacities, viewmatrices, projmatrices, camposs, tanfovx, tanfovy, image_height, image_width,
+                    bg, sh_degree=0, shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None,
+                    means2D=None, scale_modifier=1.0):
+    """Render V cameras of one Gaussian set in ONE call (one preprocess/sort/blend launch set, one host sync).
+
+    viewmatrices/projmatrices [V,4,4], camposs [V,3], tanfovx/tanfovy sequences of V floats.  means2D, if given,
+    is a [V,P,3] gradient sink.  Returns color [V,3,H,W], radii [V,P], depth [V,1,H,W], alpha [V,1,H,W].
+    Parameter gradients are summed over views, exactly what V separate rasterizer calls would accumulate."""
+    V = viewmatrices.shape[0]
+    if V > MAX_VIEWS:
+        outs = [rasterize_views(means3D=means3D, opacities=opacities, viewmatrices=viewmatrices[i:i + MAX_VIEWS],
+                                projmatrices=projmatrices[i:i + MAX_VIEWS], camposs=camposs[i:i + MAX_VIEWS],
+                                tanfovx=tanfovx[i:i + MAX_VIEWS], tanfovy=tanfovy[i:i + MAX_VIEWS], image_height=image_height,
+                                image_width=image_width, bg=bg, sh_degree=sh_degree, shs=shs, colors_precomp=colors_precomp,
+                                scales=scales, rotations=rotations, cov3D_precomp=cov3D_precomp,
+                                means2D=None if means2D is None else means2D[i:i + MAX_VIEWS], scale_modifier=scale_modifier)
+                for i in range(0, V, MAX_VIEWS)]
+        return tuple(torch.cat([o[k] for o in outs], 0) for k in range(4))
+    if means2D is None:
+        means2D = torch.zeros(V, means3D.shape[0], 3, dtype=torch.float32, device=means3D.device)
+    cams = (bg, viewmatrices, projmatrices, camposs, list(tanfovx), list(tanfovy), int(image_height), int(image_width),
+            int(sh_degree), float(scale_modifier), False, False)
+    return _RasterizeViews.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, cams, False)
+
+
+# ---- test / debugging access to the forward state (tile and sort indices) -----------------------------------
+def forward_with_state(**kw):
+    """Non-differentiable forward returning outputs + a dict of the intermediate buffers as torch tensors."""
+    L = load_library()
+    dev = kw["means3D"].device
+    t = lambda k: _f32c(kw.get(k), dev)
+    vm, pm, cp = kw["viewmatrix"], kw["projmatrix"], kw["campos"]
+    V = 1 if vm.dim() == 2 else vm.shape[0]
+    tanx, tany = kw["tanfovx"], kw["tanfovy"]
+    if not isinstance(tanx, (list, tuple)):
+        tanx, tany = [tanx], [tany]
+    color, radii, depth, alpha, st = _forward_impl(
+        t("means3D"), t("shs"), t("colors_precomp"), t("opacities"), t("scales"), t("rotations"), t("cov3D_precomp"),
+        _f32c(kw["bg"], dev), _f32c(vm, dev).reshape(V, 4, 4), _f32c(pm, dev).reshape(V, 4, 4), _f32c(cp, dev).reshape(V, 3),
+        tanx, tany, int(kw["image_height"]), int(kw["image_width"]), int(kw.get("sh_degree", 0)),
+        float(kw.get("scale_modifier", 1.0)))
+    sv = _StateView()
+    _check(L.b200gs_describe_state(C.byref(st.prm), _ptr(st.geom), _ptr(st.binning), st.capacity, _ptr(st.image), C.byref(sv)),
+           "describe_state")
+    P, H, W, D = st.P, st.H, st.W, st.num_rendered
+    ntiles = ((W + 15) // 16) * ((H + 15) // 16)
+
+    def view(buf, addr, dtype, count):
+        off = addr - buf.data_ptr()
+        nbytes = count * torch.empty((), dtype=dtype).element_size()
+        return buf[off:off + nbytes].view(dtype).clone()
+
+    state = dict(
+        num_rendered=D,
+        recs=view(st.geom, sv.geom_records, torch.float32, V * P * 12).reshape(V * P, 12),
+        tiles_touched=view(st.geom, sv.tiles_touched, torch.int32, V * P),
+        offsets=view(st.geom, sv.offsets, torch.int32, V * P),
+        clamped=view(st.geom, sv.clamped, torch.uint8, V * P),
+        sorted_keys=view(st.binning, sv.sorted_keys, torch.int64, D),
+        point_list=view(st.binning, sv.point_list, torch.int32, D),
+        ranges=view(st.binning, sv.ranges, torch.int32, V * ntiles * 2).reshape(V * ntiles, 2),
+        final_T=view(st.image, sv.final_T, torch.float32, V * H * W).reshape(V, H, W),
+        n_contrib=view(st.image, sv.n_contrib, torch.int32, V * H * W).reshape(V, H, W),
+    )
+    return color, radii, depth, alpha, state, st
+
+
+def device_exp(x: torch.Tensor) -> torch.Tensor:
+    """gs_exp evaluated by the CUDA library (pinned bit-for-bit against the oracle in tests)."""
+    L = load_library()
+    x = _f32c(x)
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _check(L.b200gs_test_exp(_ptr(x), _ptr(y), x.numel(), _stream(x.device)), "test_exp")
+    return y

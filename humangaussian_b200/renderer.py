@@ -1,0 +1,80 @@
+"""Render wrappers of the hot path, mirroring the reference's two entry points:
+
+  * ``render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, override_color)``
+        gaussiansplatting/gaussian_renderer/__init__.py:18-104 -- same keys in the returned dict;
+  * ``render_views(cameras, pc, bg_color)`` -- the SDS view loop of
+        threestudio/systems/GaussianDreamer.py:244-266 as ONE batched rasteriser call.
+
+``pc`` is anything with GaussianModel's getters (get_xyz, get_opacity, get_scaling, get_rotation,
+get_features, active_sh_degree) -- e.g. humangaussian_b200.scene.GaussianParams or the reference's
+own GaussianModel.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, rasterize_views
+
+
+class PipelineParams:
+    """gaussiansplatting/arguments/__init__.py:63-68"""
+    convert_SHs_python = False
+    compute_cov3D_python = False
+    debug = False
+
+
+def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_color=None):
+    xyz = pc.get_xyz
+    screenspace_points = torch.zeros_like(xyz, dtype=xyz.dtype, requires_grad=True, device=xyz.device) + 0
+    try:
+        screenspace_points.retain_grad()
+    except Exception:
+        pass
+    settings = GaussianRasterizationSettings(
+        image_height=int(viewpoint_camera.image_height), image_width=int(viewpoint_camera.image_width),
+        tanfovx=math.tan(viewpoint_camera.FoVx * 0.5), tanfovy=math.tan(viewpoint_camera.FoVy * 0.5),
+        bg=bg_color, scale_modifier=scaling_modifier, viewmatrix=viewpoint_camera.world_view_transform,
+        projmatrix=viewpoint_camera.full_proj_transform, sh_degree=pc.active_sh_degree,
+        campos=viewpoint_camera.camera_center, prefiltered=False, debug=False)
+    rasterizer = GaussianRasterizer(raster_settings=settings)
+    shs = colors = None
+    if override_color is None:
+        shs = pc.get_features
+    else:
+        colors = override_color
+    image, radii, depth, alpha = rasterizer(means3D=xyz, means2D=screenspace_points, shs=shs, colors_precomp=colors,
+                                            opacities=pc.get_opacity, scales=pc.get_scaling, rotations=pc.get_rotation,
+                                            cov3D_precomp=None)
+    return {"render": image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii,
+            "depth_3dgs": depth, "alpha_3dgs": alpha}
+
+
+def stack_cameras(cameras, device):
+    vm = torch.stack([c.world_view_transform.to(device).float() for c in cameras])
+    pm = torch.stack([c.full_proj_transform.to(device).float() for c in cameras])
+    cp = torch.stack([c.camera_center.to(device).float() for c in cameras])
+    tanx = [math.tan(c.FoVx * 0.5) for c in cameras]
+    tany = [math.tan(c.FoVy * 0.5) for c in cameras]
+    return vm, pm, cp, tanx, tany
+
+
+def render_views(cameras, pc, bg_color, scaling_modifier=1.0):
+    """All cameras share image size.  Returns the dict of `render` with a leading view axis:
+    render [V,3,H,W], depth_3dgs/alpha_3dgs [V,1,H,W], radii [V,P], viewspace_points [V,P,3]."""
+    xyz = pc.get_xyz
+    V = len(cameras)
+    vm, pm, cp, tanx, tany = stack_cameras(cameras, xyz.device)
+    screenspace_points = torch.zeros(V, xyz.shape[0], 3, dtype=xyz.dtype, device=xyz.device, requires_grad=True) + 0
+    try:
+        screenspace_points.retain_grad()
+    except Exception:
+        pass
+    image, radii, depth, alpha = rasterize_views(
+        means3D=xyz, opacities=pc.get_opacity, viewmatrices=vm, projmatrices=pm, camposs=cp, tanfovx=tanx, tanfovy=tany,
+        image_height=int(cameras[0].image_height), image_width=int(cameras[0].image_width), bg=bg_color,
+        sh_degree=pc.active_sh_degree, shs=pc.get_features, scales=pc.get_scaling, rotations=pc.get_rotation,
+        means2D=screenspace_points, scale_modifier=scaling_modifier)
+    return {"render": image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii,
+            "depth_3dgs": depth, "alpha_3dgs": alpha}

@@ -1,0 +1,145 @@
+/*
+ * b200gs.h -- C ABI of the B200-native differentiable 3D-Gaussian-splatting rasteriser.
+ *
+ * This is the drop-in boundary for HumanGaussian's hot path.  The reference binds the rasteriser as
+ * the Python package `diff_gaussian_rasterization` (an un-vendored torch C++/CUDA extension):
+ *     gaussiansplatting/gaussian_renderer/__init__.py:14        import of GaussianRasterizationSettings, GaussianRasterizer
+ *     gaussiansplatting/gaussian_renderer/__init__.py:36-51     settings -> GaussianRasterizer(raster_settings=...)
+ *     gaussiansplatting/gaussian_renderer/__init__.py:86-94     rasterizer(means3D=, means2D=, shs=, colors_precomp=, opacities=, scales=, rotations=, cov3D_precomp=)
+ *     gs_renderer.py:10-13, 951-966, 1006-1015                  same surface, animation path
+ * Upstream's extension exposes rasterize_gaussians / rasterize_gaussians_backward / mark_visible to
+ * Python; the three entry points below replace exactly those, with plain pointers and sizes
+ * (no torch types), plus a view-batched form (n_views > 1) for the SDS view loop
+ * (threestudio/systems/GaussianDreamer.py:244-248) and the animation frame loop (animation.py:1002-1013).
+ *
+ * Conventions
+ *   - every `const float*` / `float*` / `int32_t*` / `void*` buffer is DEVICE memory on the current CUDA device
+ *     unless the parameter comment says "host";
+ *   - all kernels are enqueued on `stream` (a cudaStream_t passed as void*); functions return after enqueueing,
+ *     except b200gs_forward which performs ONE stream synchronisation to read back the instance count
+ *     (upstream does the same, once per view; here it is once per batch of views);
+ *   - return value 0 = success, negative = b200gs_status; nothing throws across the ABI; no global state;
+ *   - matrices are the reference's row-vector-convention 4x4 tensors read as 16 contiguous floats
+ *     (world_view_transform / full_proj_transform, gaussiansplatting/scene/cameras.py:50-52).
+ */
+#ifndef B200GS_H
+#define B200GS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200GS_ABI_VERSION 1
+#define B200GS_MAX_VIEWS 64 /* per call; callers chunk larger batches */
+
+typedef enum b200gs_status {
+    B200GS_OK = 0,
+    B200GS_E_ARGS = -1,         /* inconsistent arguments (both/neither of shs|colors_precomp, scales+rotations|cov3D_precomp, ...) */
+    B200GS_E_BIN_TOO_SMALL = -2, /* binning buffer cannot hold the instances; *num_rendered holds the count needed: grow and call again */
+    B200GS_E_BUFFER = -3,        /* a state buffer is smaller than b200gs_*_bytes() asks for */
+    B200GS_E_CUDA = -4,          /* a CUDA call failed; see b200gs_last_cuda_error() */
+    B200GS_E_RANGE = -5          /* sizes outside supported range (sh_degree > 3, n_views > B200GS_MAX_VIEWS, > 2^32-1 instances) */
+} b200gs_status;
+
+/* Mirrors GaussianRasterizationSettings (12 fields; built at gaussian_renderer/__init__.py:36-49) plus sizes.
+ * tanfovx/tanfovy are per view (host arrays) because every camera of an SDS batch has its own fovy
+ * (threestudio/data/uncond.py:421-426). */
+typedef struct b200gs_params {
+    int32_t abi_version;    /* = B200GS_ABI_VERSION */
+    int32_t P;              /* number of Gaussians */
+    int32_t n_views;        /* V >= 1 cameras rendered by this call */
+    int32_t sh_degree;      /* active degree 0..3 (ignored when colors_precomp is given) */
+    int32_t sh_coeffs;      /* M = second dimension of shs [P,M,3]; M >= (sh_degree+1)^2 */
+    int32_t image_height;
+    int32_t image_width;
+    int32_t prefiltered;    /* accepted for surface parity; unused (as upstream) */
+    int32_t debug;          /* accepted for surface parity; unused */
+    float scale_modifier;
+    const float *tanfovx;   /* host, [V] */
+    const float *tanfovy;   /* host, [V] */
+} b200gs_params;
+
+/* ---- buffer sizing (bytes).  The caller owns three opaque state buffers, exactly as upstream's
+ *      geomBuffer / binningBuffer / imgBuffer tensors are owned by the autograd ctx. -------------------------- */
+size_t b200gs_geom_bytes(int32_t P, int32_t n_views);
+size_t b200gs_image_bytes(int32_t image_height, int32_t image_width, int32_t n_views);
+size_t b200gs_binning_bytes(int64_t instance_capacity, int32_t image_height, int32_t image_width, int32_t P, int32_t n_views);
+size_t b200gs_backward_scratch_bytes(int32_t P, int32_t n_views);
+
+/*
+ * Forward: preprocess (cull, project, 3D->2D covariance, SH) -> tile binning (scan, key emit, depth sort,
+ * tile ranges) -> front-to-back alpha blend.  Replaces rasterize_gaussians.
+ *   means3D [P,3]; exactly one of shs [P,M,3] | colors_precomp [P,3]; opacities [P] (post-sigmoid);
+ *   exactly one of (scales [P,3] post-exp AND rotations [P,4] (w,x,y,z)) | cov3D_precomp [P,6];
+ *   bg [3]; viewmatrix [V,16]; projmatrix [V,16]; campos [V,3].
+ * Outputs: out_color [V,3,H,W]; out_depth [V,1,H,W]; out_alpha [V,1,H,W]; radii [V,P] int32.
+ * instance_capacity = the capacity binning_buf was sized for with b200gs_binning_bytes().
+ * num_rendered (host, int64[1]) receives the total number of (Gaussian,tile) instances over all views;
+ * if it exceeds instance_capacity the call returns B200GS_E_BIN_TOO_SMALL before binning (grow, call again).
+ */
+int b200gs_forward(const b200gs_params *prm,
+                   const float *means3D, const float *shs, const float *colors_precomp, const float *opacities,
+                   const float *scales, const float *rotations, const float *cov3D_precomp,
+                   const float *bg, const float *viewmatrix, const float *projmatrix, const float *campos,
+                   float *out_color, float *out_depth, float *out_alpha, int32_t *radii,
+                   void *geom_buf, size_t geom_bytes,
+                   void *binning_buf, size_t binning_bytes, int64_t instance_capacity,
+                   void *image_buf, size_t image_bytes,
+                   int64_t *num_rendered, void *stream);
+
+/*
+ * Backward: back-to-front blend replay with per-Gaussian gradient accumulation -> conic/cov2D backward ->
+ * projection / depth / SH / cov3D backward.  Replaces rasterize_gaussians_backward.  Uses the three state
+ * buffers written by the matching b200gs_forward call (same prm, same inputs).
+ *   dL_dcolor [V,3,H,W]; dL_ddepth [V,1,H,W]; dL_dalpha [V,1,H,W]  (any may be NULL = zero).
+ * Gradient outputs (overwritten, not accumulated).  Parameter gradients are summed over the V views:
+ *   dL_dmeans3D [P,3]; dL_dmeans2D [V,P,3] (xy in NDC units, z = 0: the densification signal,
+ *   GaussianDreamer.py:385-391); dL_dsh [P,M,3] | dL_dcolors [P,3]; dL_dopacity [P];
+ *   dL_dscales [P,3] + dL_drots [P,4] | dL_dcov3D [P,6].
+ */
+int b200gs_backward(const b200gs_params *prm,
+                    const float *means3D, const float *shs, const float *colors_precomp, const float *opacities,
+                    const float *scales, const float *rotations, const float *cov3D_precomp,
+                    const float *bg, const float *viewmatrix, const float *projmatrix, const float *campos,
+                    const int32_t *radii,
+                    const void *geom_buf, const void *binning_buf, int64_t instance_capacity,
+                    const void *image_buf, int64_t num_rendered,
+                    const float *dL_dcolor, const float *dL_ddepth, const float *dL_dalpha,
+                    float *dL_dmeans3D, float *dL_dmeans2D, float *dL_dsh, float *dL_dcolors, float *dL_dopacity,
+                    float *dL_dscales, float *dL_drots, float *dL_dcov3D,
+                    void *scratch, size_t scratch_bytes, void *stream);
+
+/* Frustum test only (upstream markVisible): present[i] = 1 if p_view.z > 0.2 for view 0.  positions [P,3]. */
+int b200gs_mark_visible(int32_t P, const float *positions, const float *viewmatrix, const float *projmatrix,
+                        uint8_t *present, void *stream);
+
+/* ---- introspection of the state buffers, for parity tests (tile/sort indices must match bit-for-bit) ------- */
+typedef struct b200gs_state_view {
+    const void *geom_records;     /* [V*P] x 48 B: px,py,hx,hy | conicA,conicB,conicC,opacity | r,g,b,depth */
+    const uint32_t *tiles_touched;/* [V*P] */
+    const uint32_t *offsets;      /* [V*P] inclusive scan of tiles_touched */
+    const uint8_t *clamped;       /* [V*P] bit c set = channel c clamped at 0 */
+    const uint64_t *sorted_keys;  /* [num_rendered] ((view*tiles + tile) << 32) | depth bits */
+    const uint32_t *point_list;   /* [num_rendered] Gaussian index of each sorted instance */
+    const uint32_t *ranges;       /* [V*tiles][2] */
+    const float *final_T;         /* [V,H,W] */
+    const uint32_t *n_contrib;    /* [V,H,W] */
+} b200gs_state_view;
+int b200gs_describe_state(const b200gs_params *prm, const void *geom_buf, const void *binning_buf,
+                          int64_t instance_capacity, const void *image_buf, b200gs_state_view *out);
+
+/* The deterministic exp used by the blend kernels, evaluated on the device for n floats (parity pin vs oracle). */
+int b200gs_test_exp(const float *x, float *y, int64_t n, void *stream);
+
+const char *b200gs_last_cuda_error(void);
+int b200gs_abi_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t b200gs_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GS_H */

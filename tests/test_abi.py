@@ -1,0 +1,72 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/b200gs.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from util import ROOT
+
+LIB = os.path.join(ROOT, "humangaussian_b200", "libb200gs.so")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(LIB):
+        import __graft_entry__ as g
+        g.build()
+    return ctypes.CDLL(LIB)
+
+
+def test_every_declared_symbol_is_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "b200gs.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(b200gs_[a-z_0-9]+)\s*\(", hdr))
+    assert {"b200gs_forward", "b200gs_backward", "b200gs_mark_visible"} <= declared
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/b200gs.h but not exported"
+    from humangaussian_b200 import rasterizer
+    assert set(rasterizer.EXPORTS) == declared
+
+
+def test_size_queries_are_sane(lib):
+    sz, i32, i64 = ctypes.c_size_t, ctypes.c_int32, ctypes.c_int64
+    lib.b200gs_geom_bytes.restype = sz; lib.b200gs_geom_bytes.argtypes = [i32, i32]
+    lib.b200gs_image_bytes.restype = sz; lib.b200gs_image_bytes.argtypes = [i32, i32, i32]
+    lib.b200gs_binning_bytes.restype = sz; lib.b200gs_binning_bytes.argtypes = [i64, i32, i32, i32, i32]
+    lib.b200gs_backward_scratch_bytes.restype = sz; lib.b200gs_backward_scratch_bytes.argtypes = [i32, i32]
+    assert lib.b200gs_abi_version() == 1
+    assert lib.b200gs_geom_bytes(1000, 1) >= 1000 * (48 + 4 + 4 + 8 + 1)
+    assert lib.b200gs_geom_bytes(1000, 4) >= 4 * 1000 * 65
+    assert lib.b200gs_image_bytes(64, 64, 2) >= 2 * 64 * 64 * 8
+    a, b = lib.b200gs_binning_bytes(1000, 64, 64, 100, 1), lib.b200gs_binning_bytes(100000, 64, 64, 100, 1)
+    assert b > a >= 1000 * 24
+    assert lib.b200gs_backward_scratch_bytes(1000, 2) >= 2000 * 48
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under humangaussian_b200/ or diff_gaussian_rasterization/ may touch it."""
+    for pkg in ("humangaussian_b200", "diff_gaussian_rasterization"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, pkg)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports oracle/"
+                    assert "libgs_oracle" not in src and "gso_" not in src, f"{f} links the oracle"
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from humangaussian_b200 import rasterizer
+    monkeypatch.setattr(rasterizer, "_lib", None)
+    monkeypatch.setattr(rasterizer, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU/PyTorch fallback"):
+        rasterizer.load_library()
+
+
+def test_cpu_tensors_are_rejected():
+    import torch
+    from humangaussian_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+    s = GaussianRasterizationSettings(16, 16, 1.0, 1.0, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 0, torch.zeros(3), False, False)
+    z = torch.zeros
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        GaussianRasterizer(s)(means3D=z(4, 3), means2D=z(4, 3), shs=z(4, 1, 3), opacities=z(4, 1), scales=z(4, 3), rotations=z(4, 4))

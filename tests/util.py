@@ -47,3 +47,13 @@ def close(a, b, atol=1e-5, rtol=1e-4):
     err = np.abs(a - b)
     lim = atol + rtol * np.abs(b)
     return bool((err <= lim).all()), float((err / lim).max()) if err.size else 0.0
+
+
+def close_rows(a, b, atol=1e-5, rtol=1e-4):
+    """Like close(), but the relative term uses each row's largest magnitude: for float32-vs-float64 checks where one
+    component of a per-Gaussian gradient vector is a cancellation of terms the size of its neighbours."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    a2, b2 = a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1)
+    err = np.abs(a2 - b2)
+    lim = atol + rtol * np.abs(b2).max(axis=1, keepdims=True)
+    return bool((err <= lim).all()), float((err / lim).max()) if err.size else 0.0
