@@ -11,6 +11,37 @@
 static thread_local char g_err[256] = "";
 static std::atomic<int64_t> g_launches{0};
 
+// ---- optional per-stage CUDA-event timing (bench.py's roofline numbers; events sit on the launch stream) ----
+#include <mutex>
+#include <vector>
+struct StageSpan { int stage; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<StageSpan> g_spans;
+static std::vector<cudaEvent_t> g_event_pool;
+static cudaEvent_t prof_event()
+{
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct StageTimer {
+    bool on; StageSpan sp; cudaStream_t st;
+    StageTimer(int stage, cudaStream_t s) : on(g_prof_on), st(s)
+    {
+        if (!on) return;
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        sp.stage = stage; sp.e0 = prof_event(); sp.e1 = prof_event();
+        cudaEventRecord(sp.e0, st);
+    }
+    ~StageTimer()
+    {
+        if (!on) return;
+        cudaEventRecord(sp.e1, st);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_spans.push_back(sp);
+    }
+};
+
 static int cuda_fail(cudaError_t e, const char *where)
 {
     snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
@@ -86,20 +117,25 @@ int b200gs_forward(const b200gs_params *prm, const float *means3D, const float *
         for (int v = 0; v < V; v++) { a.tanfovx[v] = prm->tanfovx[v]; a.tanfovy[v] = prm->tanfovy[v]; }
         a.radii = radii; a.recs = (GeomRec *)(gb + GL.recs); a.tiles_touched = (uint32_t *)(gb + GL.tiles_touched);
         a.rects = (uint2 *)(gb + GL.rects); a.clamped = (uint8_t *)(gb + GL.clamped);
-        launch_preprocess_fwd(a, V, st);
+        { StageTimer t(B200GS_STAGE_PREPROCESS, st); launch_preprocess_fwd(a, V, st); }
         g_launches += 1;
         uint32_t *offsets = (uint32_t *)(gb + GL.offsets);
         const int64_t n_vp = (int64_t)P * V;
-        if (launch_scan_tiles(a.tiles_touched, offsets, n_vp, bb + BL.temp, BL.temp_bytes, st)) return cuda_fail(cudaGetLastError(), "scan");
-        g_launches += 2;
+        {
+            StageTimer t(B200GS_STAGE_SCAN, st);
+            if (launch_scan_tiles(a.tiles_touched, offsets, n_vp, bb + BL.temp, BL.temp_bytes, st)) return cuda_fail(cudaGetLastError(), "scan");
+        }
         uint32_t total = 0;
         CK(cudaMemcpyAsync(&total, offsets + (n_vp - 1), 4, cudaMemcpyDeviceToHost, st), "D2H num_rendered");
         CK(cudaStreamSynchronize(st), "sync after scan");
         *num_rendered = (int64_t)total;
         if ((int64_t)total > instance_capacity) return B200GS_E_BIN_TOO_SMALL;
         int nl = 0;
-        if (launch_binning(a.recs, a.rects, offsets, P, V, gx, gy, (int64_t)total, bb, BL, st, &nl)) return cuda_fail(cudaGetLastError(), "binning");
-        g_launches += nl + (total ? 4 : 0);
+        {
+            StageTimer t(B200GS_STAGE_BINNING, st);
+            if (launch_binning(a.recs, a.rects, offsets, P, V, gx, gy, (int64_t)total, bb, BL, st, &nl)) return cuda_fail(cudaGetLastError(), "binning");
+        }
+        g_launches += nl; // our emit + ranges kernels (CUB's internal launches are library code, not counted)
     }
     BlendArgs b;
     b.H = H; b.W = W; b.grid_x = gx; b.grid_y = gy; b.V = V; b.P = P;
@@ -108,7 +144,7 @@ int b200gs_forward(const b200gs_params *prm, const float *means3D, const float *
     b.final_T = (float *)(ib + IL.final_T); b.n_contrib = (uint32_t *)(ib + IL.n_contrib);
     b.out_color = out_color; b.out_depth = out_depth; b.out_alpha = out_alpha;
     (void)HW;
-    launch_blend_fwd(b, st);
+    { StageTimer t(B200GS_STAGE_BLEND_FWD, st); launch_blend_fwd(b, st); }
     g_launches += 1;
     CK(cudaGetLastError(), "forward launch");
     return B200GS_OK;
@@ -149,7 +185,7 @@ int b200gs_backward(const b200gs_params *prm, const float *means3D, const float 
     b.final_T = (const float *)(ib + IL.final_T); b.n_contrib = (const uint32_t *)(ib + IL.n_contrib);
     b.dL_dcolor = dL_dcolor; b.dL_ddepth = dL_ddepth; b.dL_dalpha = dL_dalpha;
     b.sgrad = (ScreenGrad *)scratch;
-    launch_blend_bwd(b, st);
+    { StageTimer t(B200GS_STAGE_BLEND_BWD, st); launch_blend_bwd(b, st); }
 
     PreBwdArgs a;
     a.P = P; a.V = V; a.deg = shs ? prm->sh_degree : 0; a.M = prm->sh_coeffs; a.H = H; a.W = W; a.mod = prm->scale_modifier;
@@ -159,7 +195,7 @@ int b200gs_backward(const b200gs_params *prm, const float *means3D, const float 
     a.radii = radii; a.clamped = (const uint8_t *)(gb + GL.clamped); a.sgrad = (const ScreenGrad *)scratch;
     a.dL_dmeans3D = dL_dmeans3D; a.dL_dmeans2D = dL_dmeans2D; a.dL_dsh = dL_dsh; a.dL_dcolors = dL_dcolors;
     a.dL_dopacity = dL_dopacity; a.dL_dscales = dL_dscales; a.dL_drots = dL_drots; a.dL_dcov3D = dL_dcov3D;
-    launch_preprocess_bwd(a, st);
+    { StageTimer t(B200GS_STAGE_PREPROCESS_BWD, st); launch_preprocess_bwd(a, st); }
     g_launches += 2;
     CK(cudaGetLastError(), "backward launch");
     return B200GS_OK;
@@ -196,6 +232,28 @@ int b200gs_describe_state(const b200gs_params *prm, const void *geom_buf, const 
     out->ranges = (const uint32_t *)(bb + BL.ranges);
     out->final_T = (const float *)(ib + IL.final_T);
     out->n_contrib = (const uint32_t *)(ib + IL.n_contrib);
+    return B200GS_OK;
+}
+
+void b200gs_profile_enable(int on)
+{
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on != 0;
+}
+
+int b200gs_profile_read(double *ms_per_stage, int64_t *calls_per_stage, int32_t n_stages)
+{
+    if (!ms_per_stage || !calls_per_stage || n_stages < B200GS_STAGE_COUNT) return B200GS_E_ARGS;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int i = 0; i < n_stages; i++) { ms_per_stage[i] = 0.0; calls_per_stage[i] = 0; }
+    for (auto &sp : g_spans) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventSynchronize(sp.e1);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, sp.e0, sp.e1);
+        if (e == cudaSuccess) { ms_per_stage[sp.stage] += ms; calls_per_stage[sp.stage] += 1; }
+        g_event_pool.push_back(sp.e0); g_event_pool.push_back(sp.e1);
+    }
+    g_spans.clear();
     return B200GS_OK;
 }
 

@@ -321,9 +321,10 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(PreBwdArgs a)
         const float denom = ca * cc - cb * cb;
         const float d2inv = 1.0f / (denom * denom + 0.0000001f);
         if (d2inv != 0.f) {
-            const float da = d2inv * (-cc * cc * dA + 2.f * cb * cc * dBh + (denom - ca * cc) * dC);
-            const float dc = d2inv * (-ca * ca * dC + 2.f * ca * cb * dBh + (denom - ca * cc) * dA);
-            const float db = d2inv * 2.f * (cb * cc * dA - (denom + 2.f * cb * cb) * dBh + ca * cb * dC);
+            // (denom - a*c) == -b*b and (denom + 2*b*b) == a*c + b*b, written without the cancellation
+            const float da = d2inv * (-cc * cc * dA + 2.f * cb * cc * dBh - cb * cb * dC);
+            const float dc = d2inv * (-ca * ca * dC + 2.f * ca * cb * dBh - cb * cb * dA);
+            const float db = d2inv * 2.f * (cb * cc * dA - (ca * cc + cb * cb) * dBh + ca * cb * dC);
             dcov[0] += M0[0] * M0[0] * da + M0[0] * M1[0] * db + M1[0] * M1[0] * dc;
             dcov[3] += M0[1] * M0[1] * da + M0[1] * M1[1] * db + M1[1] * M1[1] * dc;
             dcov[5] += M0[2] * M0[2] * da + M0[2] * M1[2] * db + M1[2] * M1[2] * dc;

@@ -46,7 +46,8 @@ class _StateView(C.Structure):
 _lib = None
 EXPORTS = ["b200gs_forward", "b200gs_backward", "b200gs_mark_visible", "b200gs_describe_state", "b200gs_test_exp",
            "b200gs_geom_bytes", "b200gs_image_bytes", "b200gs_binning_bytes", "b200gs_backward_scratch_bytes",
-           "b200gs_last_cuda_error", "b200gs_abi_version", "b200gs_launch_count"]
+           "b200gs_last_cuda_error", "b200gs_abi_version", "b200gs_launch_count", "b200gs_profile_enable", "b200gs_profile_read"]
+STAGES = ["preprocess_fwd", "scan", "binning", "blend_fwd", "blend_bwd", "preprocess_bwd"]
 
 
 def load_library():
@@ -78,12 +79,27 @@ def load_library():
     L.b200gs_test_exp.argtypes = [vp, vp, i64, vp]
     L.b200gs_last_cuda_error.restype = C.c_char_p
     L.b200gs_launch_count.restype = i64
+    L.b200gs_profile_enable.restype = None; L.b200gs_profile_enable.argtypes = [C.c_int]
+    L.b200gs_profile_read.restype = C.c_int
+    L.b200gs_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(i64), i32]
     _lib = L
     return L
 
 
 def launch_count() -> int:
     return int(load_library().b200gs_launch_count())
+
+
+def profile_enable(on: bool):
+    load_library().b200gs_profile_enable(int(bool(on)))
+
+
+def profile_read():
+    """{stage: (total_ms, calls)} accumulated since the last read (CUDA events on the launch stream)."""
+    n = len(STAGES)
+    ms, calls = (C.c_double * n)(), (C.c_int64 * n)()
+    _check(load_library().b200gs_profile_read(ms, calls, n), "profile_read")
+    return {STAGES[i]: (float(ms[i]), int(calls[i])) for i in range(n)}
 
 
 def _check(rc, what):
@@ -113,6 +129,14 @@ def _stream(device):
 
 # instance-capacity hint per (device, P, V, H, W): avoids the retry after the first call
 _cap_hint: dict = {}
+
+
+_last_num_rendered = 0
+
+
+def last_num_rendered() -> int:
+    """Instance count D of the most recent forward call in this process (workload statistic for bench.py)."""
+    return _last_num_rendered
 
 
 class _Ctx:
@@ -165,6 +189,8 @@ def _forward_impl(means3D, shs, colors_precomp, opacities, scales, rotations, co
             cap = int(n_out.value * 1.25) + 1024
         _check(rc, "forward")
     _cap_hint[key] = max(int(n_out.value * 1.25) + 1024, 1 << 16)
+    global _last_num_rendered
+    _last_num_rendered = int(n_out.value)
     st = _Ctx()
     st.prm, st.tanx, st.tany = prm, tx, ty
     st.geom, st.binning, st.image, st.capacity, st.num_rendered = geom, binning, image, cap, int(n_out.value)

@@ -134,6 +134,14 @@ int b200gs_describe_state(const b200gs_params *prm, const void *geom_buf, const 
 /* The deterministic exp used by the blend kernels, evaluated on the device for n floats (parity pin vs oracle). */
 int b200gs_test_exp(const float *x, float *y, int64_t n, void *stream);
 
+/* ---- per-stage device timing (CUDA events recorded on the launch stream around each stage) -----------------
+ * enable, run any number of forward/backward calls, then read: accumulated milliseconds and call counts per stage
+ * since the last read.  b200gs_profile_read synchronises on the recorded events. */
+enum { B200GS_STAGE_PREPROCESS = 0, B200GS_STAGE_SCAN = 1, B200GS_STAGE_BINNING = 2, B200GS_STAGE_BLEND_FWD = 3,
+       B200GS_STAGE_BLEND_BWD = 4, B200GS_STAGE_PREPROCESS_BWD = 5, B200GS_STAGE_COUNT = 6 };
+void b200gs_profile_enable(int on);
+int b200gs_profile_read(double *ms_per_stage /* host [B200GS_STAGE_COUNT] */, int64_t *calls_per_stage /* host */, int32_t n_stages);
+
 const char *b200gs_last_cuda_error(void);
 int b200gs_abi_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */

