@@ -34,9 +34,11 @@ sys.path.insert(0, ROOT)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "classic"],
+                    help="b200 = this repo's CUDA path; reference = the reference algorithm on the host CPU (oracle port); "
+                         "classic = baseline/libb200gs_classic.so, the classic-structure CUDA comparator, through the same host path")
     ap.add_argument("--views", type=int, default=64)
     ap.add_argument("--gaussians", type=int, default=300000)
     ap.add_argument("--res", type=int, default=1024)
@@ -256,7 +258,7 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(flat.grad)  # the path's one exchange step: packed gradients, NCCL over NVLink
         if e2e:  # host buffers out: loss + packed gradients
-            stats["loss"] = float(loss)
+            stats["loss"] = float(loss.detach())
             host_grad.copy_(flat.grad, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         stats["n_vis"] = r
@@ -355,7 +357,7 @@ def run_b200(args):
                "torch_cpu_paths": torch_cpu_paths(args)}
 
     if rank == 0:
-        line = {"metric": "fwd+bwd views/sec @1024^2, ~300k Gaussians", "value": value, "unit": "views/s", "n_gpus": world,
+        line = {"impl": args.impl, "metric": "fwd+bwd views/sec @1024^2, ~300k Gaussians", "value": value, "unit": "views/s", "n_gpus": world,
                 "steps": args.steps, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
                 "views_per_step_per_gpu": V, "instances_per_step": D, "visible_per_step": n_vis,
@@ -370,6 +372,9 @@ def run_b200(args):
 
 def main():
     args = parse()
+    if args.impl == "classic":
+        os.environ["B200GS_LIB"] = os.path.join(ROOT, "baseline", "libb200gs_classic.so")
+        args.no_cpu_baseline = True
     if args.impl == "reference":
         run_reference(args)
     else:

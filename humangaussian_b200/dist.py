@@ -1,0 +1,91 @@
+"""Multi-GPU host logic of the hot path: renders are independent per (Gaussian buffer, camera),
+so views / animation frames shard across ranks and the rasteriser itself never communicates.
+
+One process per GPU (torchrun); `torch.distributed` backend "nccl" on GPUs, "gloo" in the CPU tests.
+  * pack / unpack       -- one flat SoA buffer [xyz | scale | rot | opacity | sh] = what is broadcast / all-reduced
+  * broadcast_scene     -- once per parameter version (4*(11+3K)*P bytes: 70.8 MB at P=300k, deg 3)
+  * shard_views         -- SDS batch: round-robin (GaussianDreamer.py:244-248); animation: contiguous blocks (animation.py:1002-1013)
+  * allreduce_gradients -- training only: one all-reduce of the packed gradient buffer; radii by MAX (GaussianDreamer.py:253-256)
+  * gather_frames       -- animation: finished frames back to rank 0 in frame order
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+import torch.distributed as dist
+
+FIELDS = ("xyz", "scaling", "rotation", "opacity", "features")
+
+
+def field_shapes(P: int, sh_coeffs: int):
+    return {"xyz": (P, 3), "scaling": (P, 3), "rotation": (P, 4), "opacity": (P, 1), "features": (P, sh_coeffs, 3)}
+
+
+def pack(tensors: dict) -> torch.Tensor:
+    return torch.cat([tensors[k].reshape(-1) for k in FIELDS])
+
+
+def unpack(flat: torch.Tensor, P: int, sh_coeffs: int) -> dict:
+    """Contiguous VIEWS into the flat buffer (no copies): gradients written through them land in flat.grad."""
+    need = P * (11 + 3 * sh_coeffs)
+    if flat.dim() != 1 or flat.numel() != need:
+        raise ValueError(f"flat buffer has {flat.numel()} elements, layout needs {need}")
+    out, o = {}, 0
+    for k, shape in field_shapes(P, sh_coeffs).items():
+        n = 1
+        for s in shape:
+            n *= s
+        out[k] = flat.narrow(0, o, n).view(shape)
+        o += n
+    return out
+
+
+def is_dist() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def broadcast_scene(flat: torch.Tensor, src: int = 0) -> torch.Tensor:
+    if is_dist():
+        dist.broadcast(flat, src)
+    return flat
+
+
+def shard_views(n_views: int, rank: int, world: int, mode: str = "round_robin") -> List[int]:
+    if mode == "round_robin":
+        return list(range(rank, n_views, world))
+    if mode == "contiguous":
+        per, rem = divmod(n_views, world)
+        start = rank * per + min(rank, rem)
+        return list(range(start, start + per + (1 if rank < rem else 0)))
+    raise ValueError(mode)
+
+
+def allreduce_gradients(flat_grad: torch.Tensor, radii: torch.Tensor | None = None):
+    """Sum packed parameter gradients over ranks (and max-reduce radii) so every replica takes the same Adam /
+    densification step."""
+    if is_dist():
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+        if radii is not None:
+            dist.all_reduce(radii, op=dist.ReduceOp.MAX)
+    return flat_grad, radii
+
+
+def gather_frames(local_frames: torch.Tensor, local_ids: Sequence[int], n_frames: int, dst: int = 0):
+    """local_frames [n_local, ...] rendered for frame ids `local_ids`; returns [n_frames, ...] on dst (None elsewhere)."""
+    if not is_dist():
+        out = torch.empty((n_frames,) + tuple(local_frames.shape[1:]), dtype=local_frames.dtype, device=local_frames.device)
+        out[list(local_ids)] = local_frames
+        return out
+    world, rank = dist.get_world_size(), dist.get_rank()
+    counts = [len(shard_views(n_frames, r, world, "contiguous")) for r in range(world)]
+    if list(local_ids) != shard_views(n_frames, rank, world, "contiguous"):
+        raise ValueError("gather_frames expects the contiguous sharding of shard_views")
+    # dist.gather needs equal shapes: pad every shard to the largest one, trim on dst
+    cmax = max(counts)
+    pad = local_frames.contiguous()
+    if pad.shape[0] < cmax:
+        pad = torch.cat([pad, pad.new_zeros((cmax - pad.shape[0],) + tuple(pad.shape[1:]))], 0)
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst)
+    return torch.cat([b[:c] for b, c in zip(bufs, counts)], 0) if rank == dst else None

@@ -24,7 +24,9 @@ import torch
 from torch import nn
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200gs.so")
+# B200GS_LIB selects another build of the SAME C-ABI (only used to time baseline/libb200gs_classic.so, the
+# classic-structure comparator, through the identical host path).  It is not a fallback: the default is the product.
+LIB_PATH = os.environ.get("B200GS_LIB") or os.path.join(_HERE, "libb200gs.so")
 ABI_VERSION = 1
 MAX_VIEWS = 64
 
@@ -279,9 +281,8 @@ def _cams_from_settings(s: GaussianRasterizationSettings):
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
-    empty = lambda t: None if (t is None or t.numel() == 0) else t
-    return _RasterizeViews.apply(means3D, means2D, empty(sh), empty(colors_precomp), opacities, empty(scales), empty(rotations),
-                                 empty(cov3Ds_precomp), _cams_from_settings(raster_settings), True)
+    return _RasterizeViews.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                                 _cams_from_settings(raster_settings), True)
 
 
 class GaussianRasterizer(nn.Module):

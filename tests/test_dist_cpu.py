@@ -1,0 +1,75 @@
+"""CPU, world_size 2 over gloo: the N>1 host logic (scene broadcast, view sharding, packed-gradient all-reduce,
+frame gather).  The rasteriser itself never communicates, so a deterministic stand-in 'render' is enough here."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from humangaussian_b200 import dist as D
+
+
+def _fake_grad(flat, view_id):
+    return torch.sin(flat * (view_id + 1)) * 0.01
+
+
+def _worker(rank, world, port, n_views, P, K, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = P * (11 + 3 * K)
+        flat = torch.arange(n, dtype=torch.float32) * 1e-3 if rank == 0 else torch.zeros(n)
+        D.broadcast_scene(flat, 0)
+        f = D.unpack(flat, P, K)
+        assert f["features"].shape == (P, K, 3) and f["xyz"].data_ptr() == flat.data_ptr()
+        mine = D.shard_views(n_views, rank, world)
+        g = torch.zeros_like(flat)
+        for v in mine:
+            g += _fake_grad(flat, v)
+        radii = torch.full((P,), rank + 1, dtype=torch.int32)
+        D.allreduce_gradients(g, radii)
+        frames_ids = D.shard_views(n_views, rank, world, "contiguous")
+        frames = torch.stack([torch.full((2, 3), float(i)) for i in frames_ids])
+        gathered = D.gather_frames(frames, frames_ids, n_views, 0)
+        torch.save({"flat": flat, "grad": g, "radii": radii, "gathered": gathered, "mine": mine}, os.path.join(out_dir, f"r{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_view_sharding(tmp_path):
+    world, n_views, P, K = 2, 7, 50, 4
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, n_views, P, K, str(tmp_path)), nprocs=world, join=True)
+    r = [torch.load(tmp_path / f"r{i}.pt") for i in range(world)]
+    ref_flat = torch.arange(P * (11 + 3 * K), dtype=torch.float32) * 1e-3
+    want = sum(_fake_grad(ref_flat, v) for v in range(n_views))
+    for i in range(world):
+        assert torch.equal(r[i]["flat"], ref_flat)                      # broadcast reached every rank
+        assert torch.allclose(r[i]["grad"], want, atol=1e-6)            # sharded sum == single-process sum
+        assert int(r[i]["radii"].max()) == world                        # MAX-reduced
+    assert sorted(r[0]["mine"] + r[1]["mine"]) == list(range(n_views))  # every view rendered exactly once
+    assert r[1]["gathered"] is None
+    assert torch.equal(r[0]["gathered"][:, 0, 0], torch.arange(n_views, dtype=torch.float32))  # frame order kept
+
+
+def test_sharding_partitions():
+    for n in (1, 7, 64, 136):
+        for w in (1, 2, 4, 8):
+            for mode in ("round_robin", "contiguous"):
+                parts = [D.shard_views(n, r, w, mode) for r in range(w)]
+                assert sorted(sum(parts, [])) == list(range(n))
+                assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def test_pack_unpack_roundtrip():
+    P, K = 10, 16
+    t = {k: torch.randn(s) for k, s in D.field_shapes(P, K).items()}
+    flat = D.pack(t)
+    u = D.unpack(flat, P, K)
+    for k in t:
+        assert torch.equal(u[k], t[k])
+    with pytest.raises(ValueError):
+        D.unpack(flat[:-1], P, K)
