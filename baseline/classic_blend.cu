@@ -168,6 +168,7 @@ void launch_blend_bwd(const BlendBwdArgs &a, cudaStream_t st)
     dim3 grid(a.grid_x * a.grid_y, a.V);
     classic_bwd<<<grid, BLOCK_SIZE, 0, st>>>(a);
 }
+int blend_sgrad_is_moments() { return 0; }
 __global__ void classic_exp_kernel(const float *x, float *y, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

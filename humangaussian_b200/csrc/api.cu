@@ -193,6 +193,7 @@ int b200gs_backward(const b200gs_params *prm, const float *means3D, const float 
     a.view = viewmatrix; a.proj = projmatrix; a.campos = campos;
     for (int v = 0; v < V; v++) { a.tanfovx[v] = prm->tanfovx[v]; a.tanfovy[v] = prm->tanfovy[v]; }
     a.radii = radii; a.clamped = (const uint8_t *)(gb + GL.clamped); a.sgrad = (const ScreenGrad *)scratch;
+    a.recs = (const GeomRec *)(gb + GL.recs); a.moments = blend_sgrad_is_moments();
     a.dL_dmeans3D = dL_dmeans3D; a.dL_dmeans2D = dL_dmeans2D; a.dL_dsh = dL_dsh; a.dL_dcolors = dL_dcolors;
     a.dL_dopacity = dL_dopacity; a.dL_dscales = dL_dscales; a.dL_drots = dL_drots; a.dL_dcov3D = dL_dcov3D;
     { StageTimer t(B200GS_STAGE_PREPROCESS_BWD, st); launch_preprocess_bwd(a, st); }

@@ -25,6 +25,8 @@ struct PreBwdArgs {
     const int32_t *radii;
     const uint8_t *clamped;
     const ScreenGrad *sgrad; // [V*P]
+    const GeomRec *recs;     // [V*P] forward records (conic, opacity) -- used when sgrad holds moments
+    int moments;             // 1: sgrad = (S0,Sx,Sy,Sxx,Sxy,Syy,cr,cg,cb,cd); 0: classic (dx,dy,dA,dBh,dC,dO,dr,dg,db,dd)
     float *dL_dmeans3D, *dL_dmeans2D, *dL_dsh, *dL_dcolors, *dL_dopacity, *dL_dscales, *dL_drots, *dL_dcov3D;
 };
 
@@ -67,4 +69,5 @@ int launch_binning(const GeomRec *recs, const uint2 *rects, const uint32_t *offs
 
 void launch_blend_fwd(const BlendArgs &a, cudaStream_t st);
 void launch_blend_bwd(const BlendBwdArgs &a, cudaStream_t st);
+int blend_sgrad_is_moments(); // which ScreenGrad format the linked blend_bwd writes
 void launch_test_exp(const float *x, float *y, int64_t n, cudaStream_t st);

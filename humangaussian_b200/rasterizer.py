@@ -113,8 +113,20 @@ def _check(rc, what):
     raise RuntimeError(f"b200gs {what} failed: {msg}")
 
 
+_dummy: dict = {}
+
+
 def _ptr(t: Optional[torch.Tensor]):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    """Raw device pointer.  A zero-element tensor (P == 0) has a null data_ptr; the ABI treats NULL as "argument
+    absent", so hand it a small valid dummy allocation instead."""
+    if t is None:
+        return None
+    if t.numel() == 0:
+        key = (t.device.type, t.device.index)
+        if key not in _dummy:
+            _dummy[key] = torch.zeros(64, dtype=torch.float32, device=t.device)
+        return C.c_void_p(_dummy[key].data_ptr())
+    return C.c_void_p(t.data_ptr())
 
 
 def _f32c(t: Optional[torch.Tensor], device=None):
