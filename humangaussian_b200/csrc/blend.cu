@@ -42,30 +42,31 @@ __device__ __forceinline__ uint32_t patch_mask(float px, float py, float hx, flo
     return m;
 }
 
-// Each warp builds the ordered list of batch entries whose mask has its bit set and whose index is < limit.
-__device__ __forceinline__ int build_warp_list(const uint8_t *s_mask, uint8_t *list, int n, int warp, int lane, int limit)
+// power with the conic pre-scaled at staging time (A' = -A/2, B' = -B, C' = -C/2: exact operations, so the
+// result is bit-identical to gs_power(A,B,C,dx,dy))
+__device__ __forceinline__ float power_prescaled(float Ap, float Bp, float Cp, float dx, float dy)
 {
-    int cnt = 0;
-    const uint32_t lt = (1u << lane) - 1u;
-    for (int k = 0; k < n; k += 32) {
-        const int j = k + lane;
-        const bool hit = (j < n) && (j < limit) && ((s_mask[j] >> warp) & 1);
-        const uint32_t b = __ballot_sync(FULL, hit);
-        if (hit) list[cnt + __popc(b & lt)] = (uint8_t)j;
-        cnt += __popc(b);
-    }
-    __syncwarp();
-    return cnt;
+    const float u = ffma(Bp, dy, fmul(Ap, dx));
+    const float w = fmul(fmul(Cp, dy), dy);
+    return ffma(dx, u, w);
 }
+
+// Shared-memory tile of one batch: 256 staged records (48 B each, conic pre-scaled), their patch masks, and one
+// compacted index list per warp.  Accessed only through this struct so every access is a plain LDS/STS with an
+// immediate offset (no generic-address arithmetic in the inner loops).
+struct __align__(16) BatchSmem {
+    float4 rec[BATCH * 3];
+    uint32_t id[BATCH];
+    uint8_t mask[BATCH];
+    uint8_t list[8][BATCH];
+};
 
 // ------------------------------------------------------------------------------------------------
 // F6
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendArgs a)
 {
-    __shared__ float4 s0[BATCH], s1[BATCH], s2[BATCH];
-    __shared__ uint8_t s_mask[BATCH];
-    __shared__ uint8_t s_list[8][BATCH];
+    __shared__ BatchSmem sm;
 
     const int ntiles = a.grid_x * a.grid_y;
     const int tile = blockIdx.x, v = blockIdx.y;
@@ -80,61 +81,73 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendArgs a)
     const uint2 range = a.ranges[(size_t)v * ntiles + tile];
     const int n_total = (int)(range.y - range.x);
     const float4 *recs4 = reinterpret_cast<const float4 *>(a.recs);
+    const uint32_t lt = (1u << lane) - 1u;
 
-    bool done = !inside;
-    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dd = 0.f, Aa = 0.f;
+    // T == 0 is the "done" sentinel: a finished (or out-of-image) pixel keeps failing the T test and never
+    // accumulates, exactly like upstream's `done` flag; T_out remembers the transmittance to report.
+    float T = inside ? 1.0f : 0.0f, T_out = 1.0f;
+    float C0 = 0.f, C1 = 0.f, C2 = 0.f, Dd = 0.f, Aa = 0.f;
     uint32_t last = 0;
 
     for (int base = 0; base < n_total; base += BATCH) {
-        if (__syncthreads_count(done) == 256) break;
+        if (__syncthreads_count(T == 0.0f) == 256) break;
         const int n = min(BATCH, n_total - base);
         if (tid < n) {
             const uint32_t id = __ldg(a.point_list + range.x + base + tid);
             const float4 g0 = __ldg(recs4 + 3 * (size_t)id);
-            s0[tid] = g0;
-            s1[tid] = __ldg(recs4 + 3 * (size_t)id + 1);
-            s2[tid] = __ldg(recs4 + 3 * (size_t)id + 2);
-            s_mask[tid] = (uint8_t)patch_mask(g0.x, g0.y, g0.z, g0.w, tx0, ty0);
+            const float4 g1 = __ldg(recs4 + 3 * (size_t)id + 1);
+            sm.rec[3 * tid] = g0;
+            sm.rec[3 * tid + 1] = make_float4(fmul(-0.5f, g1.x), -g1.y, fmul(-0.5f, g1.z), g1.w);
+            sm.rec[3 * tid + 2] = __ldg(recs4 + 3 * (size_t)id + 2);
+            sm.mask[tid] = (uint8_t)patch_mask(g0.x, g0.y, g0.z, g0.w, tx0, ty0);
         }
         __syncthreads();
-        if (__all_sync(FULL, done)) continue;
-        const int cnt = build_warp_list(s_mask, s_list[warp], n, warp, lane, BATCH);
+        if (__all_sync(FULL, T == 0.0f)) continue;
+        int cnt = 0;
+        for (int k = 0; k < n; k += 32) {
+            const int j = k + lane;
+            const bool hit = (j < n) && ((sm.mask[j] >> warp) & 1);
+            const uint32_t b = __ballot_sync(FULL, hit);
+            if (hit) sm.list[warp][cnt + __popc(b & lt)] = (uint8_t)j;
+            cnt += __popc(b);
+        }
+        __syncwarp();
         for (int i = 0; i < cnt; i++) {
-            const int j = s_list[warp][i];
-            if (!done) {
-                const float4 g0 = s0[j], g1 = s1[j];
-                const float dx = fsub(g0.x, fpx), dy = fsub(g0.y, fpy);
-                const float power = gs_power(g1.x, g1.y, g1.z, dx, dy);
-                if (!(power > 0.0f)) {
-                    const float alpha = fminf(GS_ALPHA_MAX, fmul(g1.w, gs_exp(power)));
-                    if (!(alpha < GS_ALPHA_MIN)) {
-                        const float test_T = fmul(T, fsub(1.0f, alpha));
-                        if (test_T < GS_T_MIN) {
-                            done = true;
-                        } else {
-                            const float w = fmul(alpha, T);
-                            const float4 g2 = s2[j];
-                            C0 = ffma(g2.x, w, C0); C1 = ffma(g2.y, w, C1); C2 = ffma(g2.z, w, C2);
-                            Dd = ffma(g2.w, w, Dd);
-                            Aa = fadd(Aa, w);
-                            T = test_T;
-                            last = (uint32_t)(base + j + 1);
-                        }
+            const int j = sm.list[warp][i];
+            const float4 g0 = sm.rec[3 * j], g1 = sm.rec[3 * j + 1];
+            const float dx = fsub(g0.x, fpx), dy = fsub(g0.y, fpy);
+            const float power = power_prescaled(g1.x, g1.y, g1.z, dx, dy);
+            if (!(power > 0.0f)) {
+                const float alpha = fminf(GS_ALPHA_MAX, fmul(g1.w, gs_exp(power)));
+                if (!(alpha < GS_ALPHA_MIN)) {
+                    const float test_T = fmul(T, fsub(1.0f, alpha));
+                    if (test_T < GS_T_MIN) {
+                        if (T != 0.0f) T_out = T;
+                        T = 0.0f;
+                    } else {
+                        const float w = fmul(alpha, T);
+                        const float4 g2 = sm.rec[3 * j + 2];
+                        C0 = ffma(g2.x, w, C0); C1 = ffma(g2.y, w, C1); C2 = ffma(g2.z, w, C2);
+                        Dd = ffma(g2.w, w, Dd);
+                        Aa = fadd(Aa, w);
+                        T = test_T;
+                        last = (uint32_t)(base + j + 1);
                     }
                 }
             }
-            if (__all_sync(FULL, done)) break;
+            if (__all_sync(FULL, T == 0.0f)) break;
         }
     }
     if (inside) {
+        if (T != 0.0f) T_out = T;
         const size_t HW = (size_t)a.H * a.W;
         const size_t pix = (size_t)py * a.W + px;
-        a.final_T[v * HW + pix] = T;
+        a.final_T[v * HW + pix] = T_out;
         a.n_contrib[v * HW + pix] = last;
         float *oc = a.out_color + (size_t)v * 3 * HW;
-        oc[pix] = ffma(T, a.bg[0], C0);
-        oc[HW + pix] = ffma(T, a.bg[1], C1);
-        oc[2 * HW + pix] = ffma(T, a.bg[2], C2);
+        oc[pix] = ffma(T_out, a.bg[0], C0);
+        oc[HW + pix] = ffma(T_out, a.bg[1], C1);
+        oc[2 * HW + pix] = ffma(T_out, a.bg[2], C2);
         a.out_depth[v * HW + pix] = Dd;
         a.out_alpha[v * HW + pix] = Aa;
     }
@@ -183,10 +196,7 @@ __device__ __forceinline__ int slot_of_lane(int lane)
 
 __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a)
 {
-    __shared__ float4 s0[BATCH], s1[BATCH], s2[BATCH];
-    __shared__ uint32_t s_id[BATCH];
-    __shared__ uint8_t s_mask[BATCH];
-    __shared__ uint8_t s_list[8][BATCH];
+    __shared__ BatchSmem sm;
     __shared__ int s_max;
 
     const int ntiles = a.grid_x * a.grid_y;
@@ -239,11 +249,12 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a)
         if (tid < n) {
             const uint32_t id = __ldg(a.point_list + range.x + (hi - 1 - tid));
             const float4 g0 = __ldg(recs4 + 3 * (size_t)id);
-            s0[tid] = g0;
-            s1[tid] = __ldg(recs4 + 3 * (size_t)id + 1);
-            s2[tid] = __ldg(recs4 + 3 * (size_t)id + 2);
-            s_id[tid] = id;
-            s_mask[tid] = (uint8_t)patch_mask(g0.x, g0.y, g0.z, g0.w, tx0, ty0);
+            const float4 g1 = __ldg(recs4 + 3 * (size_t)id + 1);
+            sm.rec[3 * tid] = g0;
+            sm.rec[3 * tid + 1] = make_float4(fmul(-0.5f, g1.x), -g1.y, fmul(-0.5f, g1.z), g1.w);
+            sm.rec[3 * tid + 2] = __ldg(recs4 + 3 * (size_t)id + 2);
+            sm.id[tid] = id;
+            sm.mask[tid] = (uint8_t)patch_mask(g0.x, g0.y, g0.z, g0.w, tx0, ty0);
         }
         __syncthreads();
         // batch entry j sits at list position hi-1-j; it can matter to this warp only if hi-1-j < wmax
@@ -254,26 +265,26 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a)
             const uint32_t lt = (1u << lane) - 1u;
             for (int k = first & ~31; k < n; k += 32) {
                 const int j = k + lane;
-                const bool hit = (j < n) && (j >= first) && ((s_mask[j] >> warp) & 1);
+                const bool hit = (j < n) && (j >= first) && ((sm.mask[j] >> warp) & 1);
                 const uint32_t b = __ballot_sync(FULL, hit);
-                if (hit) s_list[warp][cnt + __popc(b & lt)] = (uint8_t)j;
+                if (hit) sm.list[warp][cnt + __popc(b & lt)] = (uint8_t)j;
                 cnt += __popc(b);
             }
             __syncwarp();
         }
         for (int i = 0; i < cnt; i++) {
-            const int j = s_list[warp][i];
+            const int j = sm.list[warp][i];
             const int pos = hi - 1 - j; // 0-based position in the tile list
-            const float4 g0 = s0[j], g1 = s1[j];
+            const float4 g0 = sm.rec[3 * j], g1 = sm.rec[3 * j + 1];
             const float dx = fsub(g0.x, fpx), dy = fsub(g0.y, fpy);
-            const float power = gs_power(g1.x, g1.y, g1.z, dx, dy);
+            const float power = power_prescaled(g1.x, g1.y, g1.z, dx, dy);
             const float G = gs_exp(power);
             const float alpha = fminf(GS_ALPHA_MAX, fmul(g1.w, G));
             const bool contrib = (pos < last) && !(power > 0.0f) && !(alpha < GS_ALPHA_MIN);
             if (!__any_sync(FULL, contrib)) continue;
             float q = 0.f, w = 0.f;
             if (contrib) {
-                const float4 g2 = s2[j];
+                const float4 g2 = sm.rec[3 * j + 2];
                 const float one_m_a = 1.0f - alpha;
                 const float inv = __frcp_rn(one_m_a);
                 T = T * inv;
@@ -295,7 +306,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a)
             }
             const float qx = q * dx, qy = q * dy;
             const float e = butterfly10(q, qx, qy, qx * dx, qx * dy, qy * dy, w * gC0, w * gC1, w * gC2, w * gD, lane);
-            if (slot >= 0) atomicAdd(reinterpret_cast<float *>(a.sgrad + s_id[j]) + slot, e);
+            if (slot >= 0) atomicAdd(reinterpret_cast<float *>(a.sgrad + sm.id[j]) + slot, e);
         }
     }
 }
