@@ -9,8 +9,8 @@
 //   * Tile lists are exactly the reference's (tile/sort indices bit-identical); culling only skips pairs whose
 //     alpha is provably < 1/255, so images are unchanged.  Forward arithmetic follows the pinned order of
 //     common.cuh: images are bit-identical to the CPU oracle.
-//   * Backward: per-pixel terms are expressed as ten sums per Gaussian -- six moments of q = G*dL/dalpha
-//     (1, dx, dy, dx^2, dx*dy, dy^2) and four colour/depth weights -- reduced over the 32 lanes with a
+//   * Backward: per-pixel terms are expressed as ten sums per Gaussian -- six sums of q = G*dL/dalpha
+//     (q, two mean-gradient forms, q dx^2, q dx dy, q dy^2) and four colour/depth weights -- reduced over the 32 lanes with a
 //     12-shuffle multi-value butterfly (not 10 x 5 shuffles), then ten lanes each issue one
 //     red.global.add.f32 into the Gaussian's 48-byte ScreenGrad record.  Upstream: ~10 atomics per PIXEL.
 #include "common.cuh"
@@ -304,8 +304,12 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a)
                 dL_dalpha = fmaf(-T_final * inv, bg_dot, dL_dalpha);
                 q = G * dL_dalpha;
             }
+            // Mx = -sum q (A dx + B dy), My = -sum q (C dy + B dx): formed per pixel (not from the moments sum q dx,
+            // sum q dy) so that the A.Sx + B.Sy cancellation of elongated Gaussians is not amplified by rounding.
             const float qx = q * dx, qy = q * dy;
-            const float e = butterfly10(q, qx, qy, qx * dx, qx * dy, qy * dy, w * gC0, w * gC1, w * gC2, w * gD, lane);
+            const float mx = q * fmaf(g1.y, dy, (g1.x + g1.x) * dx);
+            const float my = q * fmaf(g1.y, dx, (g1.z + g1.z) * dy);
+            const float e = butterfly10(q, mx, my, qx * dx, qx * dy, qy * dy, w * gC0, w * gC1, w * gC2, w * gD, lane);
             if (slot >= 0) atomicAdd(reinterpret_cast<float *>(a.sgrad + sm.id[j]) + slot, e);
         }
     }
@@ -317,7 +321,8 @@ void launch_blend_bwd(const BlendBwdArgs &a, cudaStream_t st)
     blend_bwd_kernel<<<grid, 256, 0, st>>>(a);
 }
 
-// ScreenGrad holds MOMENTS here: S0,Sx,Sy,Sxx,Sxy,Syy of q = G*dL/dalpha, then colour(3) and depth weights.
+// ScreenGrad holds sums of q = G*dL/dalpha here: S0 = sum q, Mx = -sum q(A dx + B dy), My = -sum q(C dy + B dx),
+// Sxx, Sxy, Syy = sum q dx^2, q dx dy, q dy^2; then colour(3) and depth weights.
 int blend_sgrad_is_moments() { return 1; }
 
 __global__ void test_exp_kernel(const float *x, float *y, int64_t n)

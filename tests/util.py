@@ -57,3 +57,26 @@ def close_rows(a, b, atol=1e-5, rtol=1e-4):
     err = np.abs(a2 - b2)
     lim = atol + rtol * np.abs(b2).max(axis=1, keepdims=True)
     return bool((err <= lim).all()), float((err / lim).max()) if err.size else 0.0
+
+
+def grads_agree(a, b, atol=1e-5, rtol=1e-4, min_elementwise=0.999):
+    """The gradient parity criterion of the GPU tests.
+
+    A per-Gaussian gradient is a float32 sum over hundreds of pixels with heavy cancellation (the mean/scale derivatives
+    are odd functions over the footprint), accumulated in a different order on the GPU (shuffle tree + float atomics)
+    than in the oracle (exact sums).  One component of a Gaussian's gradient vector can therefore be a near-zero
+    cancellation of terms the size of its siblings, where *elementwise* relative error is meaningless -- upstream's own
+    atomics have the same run-to-run behaviour.  So:
+      * every Gaussian's gradient VECTOR must satisfy |a-b| <= 1e-5 + 1e-4 * max|row of b|   (all rows, no exceptions);
+      * and the plain elementwise |a-b| <= 1e-5 + 1e-4*|b| must hold for at least 99.9 % of the elements.
+    Returns (ok, message)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    if a.size == 0:
+        return True, "empty"
+    a2, b2 = a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1)
+    err = np.abs(a2 - b2)
+    row_lim = atol + rtol * np.abs(b2).max(axis=1, keepdims=True)
+    row_worst = float((err / row_lim).max())
+    el_ok = float((err <= atol + rtol * np.abs(b2)).mean())
+    ok = row_worst <= 1.0 and el_ok >= min_elementwise
+    return ok, f"row-wise worst {row_worst:.2f}x of tolerance, elementwise pass rate {100 * el_ok:.4f}%"
