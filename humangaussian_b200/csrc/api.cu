@@ -117,13 +117,14 @@ int b200gs_forward(const b200gs_params *prm, const float *means3D, const float *
         for (int v = 0; v < V; v++) { a.tanfovx[v] = prm->tanfovx[v]; a.tanfovy[v] = prm->tanfovy[v]; }
         a.radii = radii; a.recs = (GeomRec *)(gb + GL.recs); a.tiles_touched = (uint32_t *)(gb + GL.tiles_touched);
         a.rects = (uint2 *)(gb + GL.rects); a.clamped = (uint8_t *)(gb + GL.clamped);
+        a.dkeys = (uint64_t *)(bb + BL.dkeys_in); a.order_in = (uint32_t *)(bb + BL.order_in);
         { StageTimer t(B200GS_STAGE_PREPROCESS, st); launch_preprocess_fwd(a, V, st); }
         g_launches += 1;
-        uint32_t *offsets = (uint32_t *)(gb + GL.offsets);
+        uint32_t *offsets = (uint32_t *)(gb + GL.offsets); // inclusive scan of tiles_touched in DEPTH order
         const int64_t n_vp = (int64_t)P * V;
         {
             StageTimer t(B200GS_STAGE_SCAN, st);
-            if (launch_scan_tiles(a.tiles_touched, offsets, n_vp, bb + BL.temp, BL.temp_bytes, st)) return cuda_fail(cudaGetLastError(), "scan");
+            if (launch_depth_order(a.tiles_touched, offsets, n_vp, V, bb, BL, st)) return cuda_fail(cudaGetLastError(), "depth order");
         }
         uint32_t total = 0;
         CK(cudaMemcpyAsync(&total, offsets + (n_vp - 1), 4, cudaMemcpyDeviceToHost, st), "D2H num_rendered");
@@ -133,7 +134,7 @@ int b200gs_forward(const b200gs_params *prm, const float *means3D, const float *
         int nl = 0;
         {
             StageTimer t(B200GS_STAGE_BINNING, st);
-            if (launch_binning(a.recs, a.rects, offsets, P, V, gx, gy, (int64_t)total, bb, BL, st, &nl)) return cuda_fail(cudaGetLastError(), "binning");
+            if (launch_binning(a.rects, offsets, P, V, gx, gy, (int64_t)total, bb, BL, st, &nl)) return cuda_fail(cudaGetLastError(), "binning");
         }
         g_launches += nl; // our emit + ranges kernels (CUB's internal launches are library code, not counted)
     }
@@ -228,7 +229,8 @@ int b200gs_describe_state(const b200gs_params *prm, const void *geom_buf, const 
     out->tiles_touched = (const uint32_t *)(gb + GL.tiles_touched);
     out->offsets = (const uint32_t *)(gb + GL.offsets);
     out->clamped = (const uint8_t *)(gb + GL.clamped);
-    out->sorted_keys = (const uint64_t *)(bb + BL.keys_out);
+    out->sorted_tile_keys = (const uint32_t *)(bb + BL.keys_out);
+    out->depth_order = (const uint32_t *)(bb + BL.order);
     out->point_list = (const uint32_t *)(bb + BL.vals_out);
     out->ranges = (const uint32_t *)(bb + BL.ranges);
     out->final_T = (const float *)(ib + IL.final_T);

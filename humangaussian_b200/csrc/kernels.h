@@ -14,6 +14,8 @@ struct PreArgs {
     uint32_t *tiles_touched; // [V*P]
     uint2 *rects;            // [V*P]
     uint8_t *clamped;        // [V*P]
+    uint64_t *dkeys;         // [V*P] (view << 32) | depth bits   (input of the depth pre-sort)
+    uint32_t *order_in;      // [V*P] = vp
 };
 
 struct PreBwdArgs {
@@ -57,15 +59,18 @@ void launch_preprocess_fwd(const PreArgs &a, int V, cudaStream_t st);
 void launch_preprocess_bwd(const PreBwdArgs &a, cudaStream_t st);
 void launch_mark_visible(int P, const float *pos, const float *V, uint8_t *present, cudaStream_t st);
 
-// binning: inclusive scan, key emission, sort, tile ranges
+// binning: depth pre-sort of the V*P Gaussians, scan in depth order, tile-key emission, stable tile sort, ranges
 struct BinLayout {
-    size_t keys_in, keys_out, vals_in, vals_out, ranges, temp, total;
+    size_t keys_in, keys_out, vals_in, vals_out, ranges; // per-instance tile keys (u32) / record indices (u32), tile ranges
+    size_t dkeys_in, dkeys_out, order_in, order;         // per-Gaussian (view|depth) keys (u64) and the depth order (u32)
+    size_t temp, total;
     size_t temp_bytes;
 };
 BinLayout binning_layout(int64_t capacity, int ntiles_total, int64_t n_vp);
-int launch_scan_tiles(const uint32_t *tiles_touched, uint32_t *offsets, int64_t n, void *temp, size_t temp_bytes, cudaStream_t st);
-int launch_binning(const GeomRec *recs, const uint2 *rects, const uint32_t *offsets, int P, int V, int grid_x, int grid_y,
-                   int64_t D, char *bin_base, const BinLayout &L, cudaStream_t st, int *n_launches);
+int launch_depth_order(const uint32_t *tiles_touched, uint32_t *offsets_sorted, int64_t n_vp, int V, char *bin_base,
+                       const BinLayout &L, cudaStream_t st);
+int launch_binning(const uint2 *rects, const uint32_t *offsets_sorted, int P, int V, int grid_x, int grid_y, int64_t D,
+                   char *bin_base, const BinLayout &L, cudaStream_t st, int *n_launches);
 
 void launch_blend_fwd(const BlendArgs &a, cudaStream_t st);
 void launch_blend_bwd(const BlendBwdArgs &a, cudaStream_t st);

@@ -41,8 +41,8 @@ class _Params(C.Structure):
 
 
 class _StateView(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("geom_records", "tiles_touched", "offsets", "clamped", "sorted_keys",
-                                          "point_list", "ranges", "final_T", "n_contrib")]
+    _fields_ = [(n, C.c_void_p) for n in ("geom_records", "tiles_touched", "offsets", "clamped", "sorted_tile_keys",
+                                          "depth_order", "point_list", "ranges", "final_T", "n_contrib")]
 
 
 _lib = None
@@ -382,12 +382,17 @@ def forward_with_state(**kw):
         tiles_touched=view(st.geom, sv.tiles_touched, torch.int32, V * P),
         offsets=view(st.geom, sv.offsets, torch.int32, V * P),
         clamped=view(st.geom, sv.clamped, torch.uint8, V * P),
-        sorted_keys=view(st.binning, sv.sorted_keys, torch.int64, D),
+        sorted_tile_keys=view(st.binning, sv.sorted_tile_keys, torch.int32, D),
+        depth_order=view(st.binning, sv.depth_order, torch.int32, V * P),
         point_list=view(st.binning, sv.point_list, torch.int32, D),
         ranges=view(st.binning, sv.ranges, torch.int32, V * ntiles * 2).reshape(V * ntiles, 2),
         final_T=view(st.image, sv.final_T, torch.float32, V * H * W).reshape(V, H, W),
         n_contrib=view(st.image, sv.n_contrib, torch.int32, V * H * W).reshape(V, H, W),
     )
+    # the reference's 64-bit sort key of every instance: (view*tiles + tile) << 32 | depth bits of its Gaussian
+    dbits = state["recs"][:, 11].contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    pl = state["point_list"].to(torch.int64) & 0xFFFFFFFF
+    state["sorted_keys"] = ((state["sorted_tile_keys"].to(torch.int64) & 0xFFFFFFFF) << 32) | dbits[pl]
     return color, radii, depth, alpha, state, st
 
 

@@ -120,9 +120,11 @@ int b200gs_mark_visible(int32_t P, const float *positions, const float *viewmatr
 typedef struct b200gs_state_view {
     const void *geom_records;     /* [V*P] x 48 B: px,py,hx,hy | conicA,conicB,conicC,opacity | r,g,b,depth */
     const uint32_t *tiles_touched;/* [V*P] */
-    const uint32_t *offsets;      /* [V*P] inclusive scan of tiles_touched */
+    const uint32_t *offsets;      /* [V*P] inclusive scan of tiles_touched taken in depth order (see depth_order) */
     const uint8_t *clamped;       /* [V*P] bit c set = channel c clamped at 0 */
-    const uint64_t *sorted_keys;  /* [num_rendered] ((view*tiles + tile) << 32) | depth bits */
+    const uint32_t *sorted_tile_keys; /* [num_rendered] view*tiles + tile of each sorted instance; the reference's 64-bit key
+                                         of instance j is (sorted_tile_keys[j] << 32) | bits(depth of record point_list[j]) */
+    const uint32_t *depth_order;  /* [V*P] record indices sorted by (view, depth bits, index) */
     const uint32_t *point_list;   /* [num_rendered] Gaussian index of each sorted instance */
     const uint32_t *ranges;       /* [V*tiles][2] */
     const float *final_T;         /* [V,H,W] */
