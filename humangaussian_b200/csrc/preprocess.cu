@@ -76,159 +76,186 @@ __device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, flo
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(hi, max(lo, v)); }
 
 // ------------------------------------------------------------------------------------------------
-// F1
+// F1.  One thread per Gaussian; the thread loads its attributes ONCE (128-bit loads for the SH block when the
+// row pitch allows), builds the 3D covariance once, then loops over the V views of the batch writing one
+// 48-byte record per view.  Per step this reads P*(44+12K) bytes instead of V times that.
+// DEG = -1: colours are given (colors_precomp), no SH.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreArgs a)
+template <int DEG>
+__global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreArgs a, int nviews)
 {
+    constexpr int NB = DEG < 0 ? 1 : (DEG + 1) * (DEG + 1);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int v = blockIdx.y;
     if (i >= a.P) return;
-    const size_t vp = (size_t)v * a.P + i;
-    const float *V = a.view + 16 * v, *PV = a.proj + 16 * v;
-
-    int radius = 0;
-    uint32_t tiles = 0;
-    uint2 rect_pack = make_uint2(0, 0);
-    uint8_t clamped = 0;
-    GeomRec rec;
-    rec.px = rec.py = 0.f; rec.hx = rec.hy = -1.f; rec.A = rec.B = rec.C = rec.o = 0.f;
-    rec.r = rec.g = rec.b = rec.depth = 0.f;
 
     const float px = __ldg(a.means + 3 * (size_t)i), py = __ldg(a.means + 3 * (size_t)i + 1),
                 pz = __ldg(a.means + 3 * (size_t)i + 2);
-    const float tx = gs_affine(V[0], V[4], V[8], V[12], px, py, pz);
-    const float ty = gs_affine(V[1], V[5], V[9], V[13], px, py, pz);
-    const float tz = gs_affine(V[2], V[6], V[10], V[14], px, py, pz);
-    do {
-        if (tz <= GS_NEAR_Z) break;
-        const float hx = gs_affine(PV[0], PV[4], PV[8], PV[12], px, py, pz);
-        const float hy = gs_affine(PV[1], PV[5], PV[9], PV[13], px, py, pz);
-        const float hw = gs_affine(PV[3], PV[7], PV[11], PV[15], px, py, pz);
-        const float pw = fdiv(1.0f, fadd(hw, 0.0000001f));
-        const float ndcx = fmul(hx, pw), ndcy = fmul(hy, pw);
-
-        float c6[6];
-        if (a.cov_pre) {
+    const float op = __ldg(a.opac + i);
+    float c6[6];
+    if (a.cov_pre) {
 #pragma unroll
-            for (int k = 0; k < 6; k++) c6[k] = __ldg(a.cov_pre + 6 * (size_t)i + k);
-        } else {
-            const float s3[3] = {__ldg(a.scales + 3 * (size_t)i), __ldg(a.scales + 3 * (size_t)i + 1),
-                                 __ldg(a.scales + 3 * (size_t)i + 2)};
-            const float4 q4 = __ldg(reinterpret_cast<const float4 *>(a.rots) + i);
-            const float q[4] = {q4.x, q4.y, q4.z, q4.w};
-            build_cov3d(s3, a.mod, q, c6);
-        }
-        const float tanx = a.tanfovx[v], tany = a.tanfovy[v];
-        const float fx = fdiv((float)a.W, fmul(2.0f, tanx)), fy = fdiv((float)a.H, fmul(2.0f, tany));
-        const float limx = fmul(1.3f, tanx), limy = fmul(1.3f, tany);
-        const float txtz = fdiv(tx, tz), tytz = fdiv(ty, tz);
-        const float cx = fmul(fminf(limx, fmaxf(-limx, txtz)), tz);
-        const float cy = fmul(fminf(limy, fmaxf(-limy, tytz)), tz);
-        const float J00 = fdiv(fx, tz), J11 = fdiv(fy, tz);
-        const float tz2 = fmul(tz, tz);
-        const float J02 = fdiv(-fmul(fx, cx), tz2), J12 = fdiv(-fmul(fy, cy), tz2);
-        float M0[3], M1[3];
+        for (int k = 0; k < 6; k++) c6[k] = __ldg(a.cov_pre + 6 * (size_t)i + k);
+    } else {
+        const float s3[3] = {__ldg(a.scales + 3 * (size_t)i), __ldg(a.scales + 3 * (size_t)i + 1),
+                             __ldg(a.scales + 3 * (size_t)i + 2)};
+        const float4 q4 = __ldg(reinterpret_cast<const float4 *>(a.rots) + i);
+        const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+        build_cov3d(s3, a.mod, q, c6);
+    }
+    float shc[3 * NB]; // SH coefficients [k][channel], or the precomputed colour
+    if (DEG < 0) {
+        shc[0] = __ldg(a.colors_pre + 3 * (size_t)i);
+        shc[1] = __ldg(a.colors_pre + 3 * (size_t)i + 1);
+        shc[2] = __ldg(a.colors_pre + 3 * (size_t)i + 2);
+    } else {
+        const float *sh = a.shs + (size_t)i * a.M * 3;
+        if ((3 * NB) % 4 == 0 && (a.M & 3) == 0) { // 16-byte aligned rows: 128-bit loads
+            const float4 *sh4 = reinterpret_cast<const float4 *>(sh);
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            M0[k] = ffma(J02, V[4 * k + 2], fmul(J00, V[4 * k + 0]));
-            M1[k] = ffma(J12, V[4 * k + 2], fmul(J11, V[4 * k + 1]));
-        }
-        const float S[3][3] = {{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}};
-        float N0[3], N1[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            N0[k] = gs_dot3(M0[0], M0[1], M0[2], S[0][k], S[1][k], S[2][k]);
-            N1[k] = gs_dot3(M1[0], M1[1], M1[2], S[0][k], S[1][k], S[2][k]);
-        }
-        const float ca = fadd(gs_dot3(N0[0], N0[1], N0[2], M0[0], M0[1], M0[2]), GS_DILATE);
-        const float cb = gs_dot3(N0[0], N0[1], N0[2], M1[0], M1[1], M1[2]);
-        const float cc = fadd(gs_dot3(N1[0], N1[1], N1[2], M1[0], M1[1], M1[2]), GS_DILATE);
-        const float det = ffma(ca, cc, -fmul(cb, cb));
-        if (det == 0.0f) break;
-        const float det_inv = fdiv(1.0f, det);
-        const float conA = fmul(cc, det_inv), conB = fmul(-cb, det_inv), conC = fmul(ca, det_inv);
-        const float mid = fmul(0.5f, fadd(ca, cc));
-        const float sq = fsqrt(fmaxf(0.1f, ffma(mid, mid, -det)));
-        const float lam = fmaxf(fadd(mid, sq), fsub(mid, sq));
-        const int rad = (int)ceilf(fmul(3.0f, fsqrt(lam)));
-        const float pxs = fmul(ffma(fadd(ndcx, 1.0f), (float)a.W, -1.0f), 0.5f);
-        const float pys = fmul(ffma(fadd(ndcy, 1.0f), (float)a.H, -1.0f), 0.5f);
-        const float fr = (float)rad;
-        const int gx = a.grid_x, gy = a.grid_y;
-        const int x0 = clampi((int)fdiv(fsub(pxs, fr), 16.0f), 0, gx);
-        const int y0 = clampi((int)fdiv(fsub(pys, fr), 16.0f), 0, gy);
-        const int x1 = clampi((int)fdiv(fsub(fadd(fadd(pxs, fr), 16.0f), 1.0f), 16.0f), 0, gx);
-        const int y1 = clampi((int)fdiv(fsub(fadd(fadd(pys, fr), 16.0f), 1.0f), 16.0f), 0, gy);
-        const int area = (x1 - x0) * (y1 - y0);
-        if (area == 0) break;
-
-        float rgb[3];
-        if (a.shs) {
-            float dx = fsub(px, a.campos[3 * v]), dy = fsub(py, a.campos[3 * v + 1]), dz = fsub(pz, a.campos[3 * v + 2]);
-            const float len = fsqrt(gs_dot3(dx, dy, dz, dx, dy, dz));
-            dx = fdiv(dx, len); dy = fdiv(dy, len); dz = fdiv(dz, len);
-            float bs[16];
-            sh_basis(a.deg, dx, dy, dz, bs);
-            const int nb = (a.deg + 1) * (a.deg + 1);
-            const float *sh = a.shs + (size_t)i * a.M * 3;
-            float acc[3] = {fmul(bs[0], __ldg(sh)), fmul(bs[0], __ldg(sh + 1)), fmul(bs[0], __ldg(sh + 2))};
-            for (int k = 1; k < nb; k++) {
-                acc[0] = ffma(bs[k], __ldg(sh + 3 * k), acc[0]);
-                acc[1] = ffma(bs[k], __ldg(sh + 3 * k + 1), acc[1]);
-                acc[2] = ffma(bs[k], __ldg(sh + 3 * k + 2), acc[2]);
-            }
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-                const float rr = fadd(acc[ch], 0.5f);
-                if (rr < 0.0f) clamped |= (1u << ch);
-                rgb[ch] = fmaxf(rr, 0.0f);
+            for (int k = 0; k < (3 * NB) / 4; k++) {
+                const float4 t = __ldg(sh4 + k);
+                shc[4 * k] = t.x; shc[4 * k + 1] = t.y; shc[4 * k + 2] = t.z; shc[4 * k + 3] = t.w;
             }
         } else {
-            rgb[0] = __ldg(a.colors_pre + 3 * (size_t)i);
-            rgb[1] = __ldg(a.colors_pre + 3 * (size_t)i + 1);
-            rgb[2] = __ldg(a.colors_pre + 3 * (size_t)i + 2);
+#pragma unroll
+            for (int k = 0; k < 3 * NB; k++) shc[k] = __ldg(sh + k);
         }
-        const float op = __ldg(a.opac + i);
-        radius = rad;
-        tiles = (uint32_t)area;
-        rect_pack = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
-        rec.px = pxs; rec.py = pys;
-        rec.A = conA; rec.B = conB; rec.C = conC; rec.o = op;
-        rec.r = rgb[0]; rec.g = rgb[1]; rec.b = rgb[2]; rec.depth = tz;
-        // Conservative half extents of {alpha >= 1/255}: power >= -tau, tau = ln(255*o).  Product-only
-        // acceleration data (never changes a result: a pixel outside [px+-hx] x [py+-hy] has
-        // alpha < 1/255 with margin far above the float error of gs_power/gs_exp).
-        {
-            const float k255 = 255.0f * op;
-            const float aniso = (ca * cc) * det_inv; // 1/(1-rho^2): amplifies rounding error of power
-            if (!(k255 > 1.0f)) {
-                rec.hx = rec.hy = -1.0f; // can never reach 1/255
-            } else if (!(aniso < 1.0e4f)) {
-                rec.hx = rec.hy = 3.0e38f; // too ill-conditioned to bound safely: never cull
+    }
+    const float S[3][3] = {{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}};
+
+    for (int v = 0; v < nviews; v++) {
+        const size_t vp = (size_t)v * a.P + i;
+        const float *V = a.view + 16 * v, *PV = a.proj + 16 * v;
+        int radius = 0;
+        uint32_t tiles = 0;
+        uint2 rect_pack = make_uint2(0, 0);
+        uint8_t clamped = 0;
+        GeomRec rec;
+        rec.px = rec.py = 0.f; rec.hx = rec.hy = -1.f; rec.A = rec.B = rec.C = rec.o = 0.f;
+        rec.r = rec.g = rec.b = rec.depth = 0.f;
+
+        const float tx = gs_affine(V[0], V[4], V[8], V[12], px, py, pz);
+        const float ty = gs_affine(V[1], V[5], V[9], V[13], px, py, pz);
+        const float tz = gs_affine(V[2], V[6], V[10], V[14], px, py, pz);
+        do {
+            if (tz <= GS_NEAR_Z) break;
+            const float hx = gs_affine(PV[0], PV[4], PV[8], PV[12], px, py, pz);
+            const float hy = gs_affine(PV[1], PV[5], PV[9], PV[13], px, py, pz);
+            const float hw = gs_affine(PV[3], PV[7], PV[11], PV[15], px, py, pz);
+            const float pw = fdiv(1.0f, fadd(hw, 0.0000001f));
+            const float ndcx = fmul(hx, pw), ndcy = fmul(hy, pw);
+
+            const float tanx = a.tanfovx[v], tany = a.tanfovy[v];
+            const float fx = fdiv((float)a.W, fmul(2.0f, tanx)), fy = fdiv((float)a.H, fmul(2.0f, tany));
+            const float limx = fmul(1.3f, tanx), limy = fmul(1.3f, tany);
+            const float txtz = fdiv(tx, tz), tytz = fdiv(ty, tz);
+            const float cx = fmul(fminf(limx, fmaxf(-limx, txtz)), tz);
+            const float cy = fmul(fminf(limy, fmaxf(-limy, tytz)), tz);
+            const float J00 = fdiv(fx, tz), J11 = fdiv(fy, tz);
+            const float tz2 = fmul(tz, tz);
+            const float J02 = fdiv(-fmul(fx, cx), tz2), J12 = fdiv(-fmul(fy, cy), tz2);
+            float M0[3], M1[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                M0[k] = ffma(J02, V[4 * k + 2], fmul(J00, V[4 * k + 0]));
+                M1[k] = ffma(J12, V[4 * k + 2], fmul(J11, V[4 * k + 1]));
+            }
+            float N0[3], N1[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                N0[k] = gs_dot3(M0[0], M0[1], M0[2], S[0][k], S[1][k], S[2][k]);
+                N1[k] = gs_dot3(M1[0], M1[1], M1[2], S[0][k], S[1][k], S[2][k]);
+            }
+            const float ca = fadd(gs_dot3(N0[0], N0[1], N0[2], M0[0], M0[1], M0[2]), GS_DILATE);
+            const float cb = gs_dot3(N0[0], N0[1], N0[2], M1[0], M1[1], M1[2]);
+            const float cc = fadd(gs_dot3(N1[0], N1[1], N1[2], M1[0], M1[1], M1[2]), GS_DILATE);
+            const float det = ffma(ca, cc, -fmul(cb, cb));
+            if (det == 0.0f) break;
+            const float det_inv = fdiv(1.0f, det);
+            const float conA = fmul(cc, det_inv), conB = fmul(-cb, det_inv), conC = fmul(ca, det_inv);
+            const float mid = fmul(0.5f, fadd(ca, cc));
+            const float sq = fsqrt(fmaxf(0.1f, ffma(mid, mid, -det)));
+            const float lam = fmaxf(fadd(mid, sq), fsub(mid, sq));
+            const int rad = (int)ceilf(fmul(3.0f, fsqrt(lam)));
+            const float pxs = fmul(ffma(fadd(ndcx, 1.0f), (float)a.W, -1.0f), 0.5f);
+            const float pys = fmul(ffma(fadd(ndcy, 1.0f), (float)a.H, -1.0f), 0.5f);
+            const float fr = (float)rad;
+            const int gx = a.grid_x, gy = a.grid_y;
+            const int x0 = clampi((int)fdiv(fsub(pxs, fr), 16.0f), 0, gx);
+            const int y0 = clampi((int)fdiv(fsub(pys, fr), 16.0f), 0, gy);
+            const int x1 = clampi((int)fdiv(fsub(fadd(fadd(pxs, fr), 16.0f), 1.0f), 16.0f), 0, gx);
+            const int y1 = clampi((int)fdiv(fsub(fadd(fadd(pys, fr), 16.0f), 1.0f), 16.0f), 0, gy);
+            const int area = (x1 - x0) * (y1 - y0);
+            if (area == 0) break;
+
+            float rgb[3];
+            if (DEG >= 0) {
+                float dx = fsub(px, a.campos[3 * v]), dy = fsub(py, a.campos[3 * v + 1]), dz = fsub(pz, a.campos[3 * v + 2]);
+                const float len = fsqrt(gs_dot3(dx, dy, dz, dx, dy, dz));
+                dx = fdiv(dx, len); dy = fdiv(dy, len); dz = fdiv(dz, len);
+                float bs[16];
+                sh_basis(DEG, dx, dy, dz, bs);
+                float acc[3] = {fmul(bs[0], shc[0]), fmul(bs[0], shc[1]), fmul(bs[0], shc[2])};
+#pragma unroll
+                for (int k = 1; k < NB; k++) {
+                    acc[0] = ffma(bs[k], shc[3 * k], acc[0]);
+                    acc[1] = ffma(bs[k], shc[3 * k + 1], acc[1]);
+                    acc[2] = ffma(bs[k], shc[3 * k + 2], acc[2]);
+                }
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) {
+                    const float rr = fadd(acc[ch], 0.5f);
+                    if (rr < 0.0f) clamped |= (1u << ch);
+                    rgb[ch] = fmaxf(rr, 0.0f);
+                }
             } else {
-                const float tau = __logf(k255) * (1.0f + 4.0e-6f * aniso) + 0.02f;
-                rec.hx = sqrtf(2.0f * tau * ca) * 1.0005f + 0.02f;
-                rec.hy = sqrtf(2.0f * tau * cc) * 1.0005f + 0.02f;
+                rgb[0] = shc[0]; rgb[1] = shc[1]; rgb[2] = shc[2];
             }
-        }
-    } while (0);
+            radius = rad;
+            tiles = (uint32_t)area;
+            rect_pack = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
+            rec.px = pxs; rec.py = pys;
+            rec.A = conA; rec.B = conB; rec.C = conC; rec.o = op;
+            rec.r = rgb[0]; rec.g = rgb[1]; rec.b = rgb[2]; rec.depth = tz;
+            // Conservative half extents of {alpha >= 1/255}: power >= -tau, tau = ln(255*o).  Product-only
+            // acceleration data (never changes a result: a pixel outside [px+-hx] x [py+-hy] has
+            // alpha < 1/255 with margin far above the float error of gs_power/gs_exp).
+            {
+                const float k255 = 255.0f * op;
+                const float aniso = (ca * cc) * det_inv; // 1/(1-rho^2): amplifies rounding error of power
+                if (!(k255 > 1.0f)) {
+                    rec.hx = rec.hy = -1.0f; // can never reach 1/255
+                } else if (!(aniso < 1.0e4f)) {
+                    rec.hx = rec.hy = 3.0e38f; // too ill-conditioned to bound safely: never cull
+                } else {
+                    const float tau = __logf(k255) * (1.0f + 4.0e-6f * aniso) + 0.02f;
+                    rec.hx = sqrtf(2.0f * tau * ca) * 1.0005f + 0.02f;
+                    rec.hy = sqrtf(2.0f * tau * cc) * 1.0005f + 0.02f;
+                }
+            }
+        } while (0);
 
-    a.radii[vp] = radius;
-    a.dkeys[vp] = ((uint64_t)v << 32) | (uint64_t)__float_as_uint(rec.depth); // culled: depth 0 sorts first, emits nothing
-    a.order_in[vp] = (uint32_t)vp;
-    a.tiles_touched[vp] = tiles;
-    a.rects[vp] = rect_pack;
-    a.clamped[vp] = clamped;
-    float4 *dst = reinterpret_cast<float4 *>(a.recs + vp);
-    dst[0] = make_float4(rec.px, rec.py, rec.hx, rec.hy);
-    dst[1] = make_float4(rec.A, rec.B, rec.C, rec.o);
-    dst[2] = make_float4(rec.r, rec.g, rec.b, rec.depth);
+        a.radii[vp] = radius;
+        a.dkeys[vp] = ((uint64_t)v << 32) | (uint64_t)__float_as_uint(rec.depth); // culled: depth 0 sorts first, emits nothing
+        a.order_in[vp] = (uint32_t)vp;
+        a.tiles_touched[vp] = tiles;
+        a.rects[vp] = rect_pack;
+        a.clamped[vp] = clamped;
+        float4 *dst = reinterpret_cast<float4 *>(a.recs + vp);
+        dst[0] = make_float4(rec.px, rec.py, rec.hx, rec.hy);
+        dst[1] = make_float4(rec.A, rec.B, rec.C, rec.o);
+        dst[2] = make_float4(rec.r, rec.g, rec.b, rec.depth);
+    }
 }
 
 void launch_preprocess_fwd(const PreArgs &a, int V, cudaStream_t st)
 {
-    dim3 grid((a.P + 255) / 256, V);
-    preprocess_fwd_kernel<<<grid, 256, 0, st>>>(a);
+    const dim3 grid((a.P + 255) / 256);
+    if (!a.shs) preprocess_fwd_kernel<-1><<<grid, 256, 0, st>>>(a, V);
+    else if (a.deg == 0) preprocess_fwd_kernel<0><<<grid, 256, 0, st>>>(a, V);
+    else if (a.deg == 1) preprocess_fwd_kernel<1><<<grid, 256, 0, st>>>(a, V);
+    else if (a.deg == 2) preprocess_fwd_kernel<2><<<grid, 256, 0, st>>>(a, V);
+    else preprocess_fwd_kernel<3><<<grid, 256, 0, st>>>(a, V);
 }
 
 __global__ void mark_visible_kernel(int P, const float *pos, const float *V, uint8_t *present)
@@ -247,12 +274,13 @@ void launch_mark_visible(int P, const float *pos, const float *V, uint8_t *prese
 // B2 + B3: one thread per Gaussian, loops over the views of the batch and SUMS parameter gradients
 // (deterministic: no atomics at the parameter level).  Plain float arithmetic (tolerance-compared).
 // ------------------------------------------------------------------------------------------------
+template <int DEG>
 __global__ void __launch_bounds__(128) preprocess_bwd_kernel(PreBwdArgs a)
 {
+    constexpr int nb = DEG < 0 ? 1 : (DEG + 1) * (DEG + 1);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.P) return;
     const float px = a.means[3 * (size_t)i], py = a.means[3 * (size_t)i + 1], pz = a.means[3 * (size_t)i + 2];
-    const int nb = (a.deg + 1) * (a.deg + 1);
 
     float c6[6];
     float R[3][3], s[3] = {0, 0, 0}, q[4] = {0, 0, 0, 0};
@@ -271,9 +299,14 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(PreBwdArgs a)
     const float S[3][3] = {{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}};
 
     float dmean[3] = {0, 0, 0}, dcov[6] = {0, 0, 0, 0, 0, 0}, dop = 0.f, dcol[3] = {0, 0, 0};
-    float dsh[48];
-    if (a.shs)
-        for (int k = 0; k < 3 * nb; k++) dsh[k] = 0.f;
+    float dsh[3 * nb], shc[3 * nb]; // SH gradient accumulators and the coefficients themselves, in registers
+#pragma unroll
+    for (int k = 0; k < 3 * nb; k++) dsh[k] = 0.f;
+    if (DEG >= 0) {
+        const float *sh = a.shs + (size_t)i * a.M * 3;
+#pragma unroll
+        for (int k = 0; k < 3 * nb; k++) shc[k] = __ldg(sh + k);
+    }
 
     for (int v = 0; v < a.V; v++) {
         const size_t vp = (size_t)v * a.P + i;
@@ -371,30 +404,30 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(PreBwdArgs a)
             dmean[k] += (PV[4 * k] * m_w - PV[4 * k + 3] * mul1) * gdx + (PV[4 * k + 1] * m_w - PV[4 * k + 3] * mul2) * gdy;
             dmean[k] += (V[4 * k + 2] - V[4 * k + 3] * mul3) * gdepth;
         }
-        if (a.shs) {
+        if (DEG >= 0) {
             const float ddx0 = px - a.campos[3 * v], ddy0 = py - a.campos[3 * v + 1], ddz0 = pz - a.campos[3 * v + 2];
             const float len = sqrtf(ddx0 * ddx0 + ddy0 * ddy0 + ddz0 * ddz0);
             const float x = ddx0 / len, y = ddy0 / len, z = ddz0 / len;
             float bs[16];
-            sh_basis(a.deg, x, y, z, bs);
+            sh_basis(DEG, x, y, z, bs);
             const uint8_t cl = a.clamped[vp];
             const float dRGB[3] = {(cl & 1) ? 0.f : gcol[0], (cl & 2) ? 0.f : gcol[1], (cl & 4) ? 0.f : gcol[2]};
-            const float *sh = a.shs + (size_t)i * a.M * 3;
             float sk[16];
+#pragma unroll
             for (int k = 0; k < nb; k++) {
                 dsh[3 * k] += bs[k] * dRGB[0];
                 dsh[3 * k + 1] += bs[k] * dRGB[1];
                 dsh[3 * k + 2] += bs[k] * dRGB[2];
-                sk[k] = sh[3 * k] * dRGB[0] + sh[3 * k + 1] * dRGB[1] + sh[3 * k + 2] * dRGB[2];
+                sk[k] = shc[3 * k] * dRGB[0] + shc[3 * k + 1] * dRGB[1] + shc[3 * k + 2] * dRGB[2];
             }
-            if (a.deg > 0) {
+            if (DEG > 0) {
                 float ddx = -SH_C1 * sk[3], ddy = -SH_C1 * sk[1], ddz = SH_C1 * sk[2];
-                if (a.deg > 1) {
+                if (DEG > 1) {
                     const float xx = x * x, yy = y * y, zz = z * z;
                     ddx += c_SH_C2[0] * y * sk[4] + c_SH_C2[2] * -2.f * x * sk[6] + c_SH_C2[3] * z * sk[7] + c_SH_C2[4] * 2.f * x * sk[8];
                     ddy += c_SH_C2[0] * x * sk[4] + c_SH_C2[1] * z * sk[5] + c_SH_C2[2] * -2.f * y * sk[6] + c_SH_C2[4] * -2.f * y * sk[8];
                     ddz += c_SH_C2[1] * y * sk[5] + c_SH_C2[2] * 4.f * z * sk[6] + c_SH_C2[3] * x * sk[7];
-                    if (a.deg > 2) {
+                    if (DEG > 2) {
                         ddx += c_SH_C3[0] * sk[9] * 6.f * x * y + c_SH_C3[1] * sk[10] * y * z + c_SH_C3[2] * sk[11] * -2.f * x * y +
                                c_SH_C3[3] * sk[12] * -6.f * x * z + c_SH_C3[4] * sk[13] * (4.f * zz - 3.f * xx - yy) +
                                c_SH_C3[5] * sk[14] * 2.f * x * z + c_SH_C3[6] * sk[15] * 3.f * (xx - yy);
@@ -420,8 +453,9 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(PreBwdArgs a)
     a.dL_dmeans3D[3 * (size_t)i + 1] = dmean[1];
     a.dL_dmeans3D[3 * (size_t)i + 2] = dmean[2];
     a.dL_dopacity[i] = dop;
-    if (a.shs) {
+    if (DEG >= 0) {
         float *o = a.dL_dsh + (size_t)i * a.M * 3;
+#pragma unroll
         for (int k = 0; k < 3 * nb; k++) o[k] = dsh[k];
         for (int k = 3 * nb; k < 3 * a.M; k++) o[k] = 0.f;
     } else {
@@ -460,5 +494,10 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(PreBwdArgs a)
 
 void launch_preprocess_bwd(const PreBwdArgs &a, cudaStream_t st)
 {
-    preprocess_bwd_kernel<<<(a.P + 127) / 128, 128, 0, st>>>(a);
+    const int grid = (a.P + 127) / 128;
+    if (!a.shs) preprocess_bwd_kernel<-1><<<grid, 128, 0, st>>>(a);
+    else if (a.deg == 0) preprocess_bwd_kernel<0><<<grid, 128, 0, st>>>(a);
+    else if (a.deg == 1) preprocess_bwd_kernel<1><<<grid, 128, 0, st>>>(a);
+    else if (a.deg == 2) preprocess_bwd_kernel<2><<<grid, 128, 0, st>>>(a);
+    else preprocess_bwd_kernel<3><<<grid, 128, 0, st>>>(a);
 }
