@@ -315,9 +315,12 @@ def run_b200(args):
     roof = None
     if D is not None:
         bytes_stage = {
-            "preprocess_fwd": V * (P * G_in + P * 8) + n_vis * G_mid,
-            "scan": V * P * 8,
-            "binning": D * 12 + D * 24 + D * 8 + V * (pix // 256) * 8,
+            # F1 reads the P Gaussians ONCE per batch (view loop inside the thread) and writes per-view state
+            "preprocess_fwd": P * G_in + V * P * 8 + n_vis * G_mid,
+            # depth pre-sort of V*P (8 B key + 4 B index, one read + one write = single-pass lower bound) + scan
+            "scan": V * P * (24 + 8),
+            # emit (8 B) + stable tile sort (single-pass bound: 8 B read + 8 B write) + ranges (4 B read + tiles*8)
+            "binning": D * 8 + D * 16 + D * 4 + V * (pix // 256) * 8,
             "blend_fwd": D * (4 + G_mid) + V * pix * 28,
             "blend_bwd": V * pix * 28 + D * (4 + G_mid) + n_vis * G_mid,
             "preprocess_bwd": n_vis * G_mid + P * G_in + P * (G_in + 12) + V * P * 12,

@@ -122,21 +122,25 @@ int b200gs_forward(const b200gs_params *prm, const float *means3D, const float *
         g_launches += 1;
         uint32_t *offsets = (uint32_t *)(gb + GL.offsets); // inclusive scan of tiles_touched in DEPTH order
         const int64_t n_vp = (int64_t)P * V;
+        const uint32_t *order_sorted = nullptr;
+        int nl = 0;
         {
             StageTimer t(B200GS_STAGE_SCAN, st);
-            if (launch_depth_order(a.tiles_touched, offsets, n_vp, V, bb, BL, st)) return cuda_fail(cudaGetLastError(), "depth order");
+            if (launch_depth_order(a.tiles_touched, offsets, n_vp, V, bb, BL, &order_sorted, st, &nl)) return cuda_fail(cudaGetLastError(), "depth order");
         }
         uint32_t total = 0;
         CK(cudaMemcpyAsync(&total, offsets + (n_vp - 1), 4, cudaMemcpyDeviceToHost, st), "D2H num_rendered");
         CK(cudaStreamSynchronize(st), "sync after scan");
         *num_rendered = (int64_t)total;
         if ((int64_t)total > instance_capacity) return B200GS_E_BIN_TOO_SMALL;
-        int nl = 0;
         {
             StageTimer t(B200GS_STAGE_BINNING, st);
-            if (launch_binning(a.rects, offsets, P, V, gx, gy, (int64_t)total, bb, BL, st, &nl)) return cuda_fail(cudaGetLastError(), "binning");
+            const int brc = launch_binning(order_sorted, a.rects, offsets, P, V, gx, gy, (int64_t)total, bb, BL, st, &nl);
+            if (brc == -3) return B200GS_E_RANGE;
+            if (brc) return cuda_fail(cudaGetLastError(), "binning");
         }
-        g_launches += nl; // our emit + ranges kernels (CUB's internal launches are library code, not counted)
+        g_launches += nl; // histogram, digit scan, onesweep passes, tile scan, emit, ranges: all ours
+        // remember where the depth order landed (ping-pong parity) for b200gs_describe_state
     }
     BlendArgs b;
     b.H = H; b.W = W; b.grid_x = gx; b.grid_y = gy; b.V = V; b.P = P;
@@ -230,7 +234,13 @@ int b200gs_describe_state(const b200gs_params *prm, const void *geom_buf, const 
     out->offsets = (const uint32_t *)(gb + GL.offsets);
     out->clamped = (const uint8_t *)(gb + GL.clamped);
     out->sorted_tile_keys = (const uint32_t *)(bb + BL.keys_out);
-    out->depth_order = (const uint32_t *)(bb + BL.order);
+    // the depth sort takes ceil((32 + bits(V)) / 8) ping-pong passes starting from order_in
+    {
+        int vb = 0;
+        while ((1 << vb) < V) vb++;
+        const int npass = (32 + vb + 7) / 8;
+        out->depth_order = (const uint32_t *)(bb + ((npass & 1) ? BL.order : BL.order_in));
+    }
     out->point_list = (const uint32_t *)(bb + BL.vals_out);
     out->ranges = (const uint32_t *)(bb + BL.ranges);
     out->final_T = (const float *)(ib + IL.final_T);
@@ -259,6 +269,20 @@ int b200gs_profile_read(double *ms_per_stage, int64_t *calls_per_stage, int32_t 
     g_spans.clear();
     return B200GS_OK;
 }
+
+int b200gs_test_sort_pairs(uint32_t *keys_a, uint32_t *keys_b, uint32_t *vals_a, uint32_t *vals_b, int64_t n, int32_t nbits,
+                           void *scratch, size_t scratch_bytes, int32_t *result_in_b, void *stream)
+{
+    if (n < 1 || nbits < 1 || nbits > 32 || !keys_a || !keys_b || !vals_a || !vals_b || !scratch || !result_in_b) return B200GS_E_ARGS;
+    if (scratch_bytes < test_sort32_scratch_bytes(n)) return B200GS_E_BUFFER;
+    int in_b = 0;
+    if (launch_test_sort32(keys_a, keys_b, vals_a, vals_b, n, nbits, (char *)scratch, scratch_bytes, &in_b, (cudaStream_t)stream))
+        return B200GS_E_RANGE;
+    *result_in_b = in_b;
+    CK(cudaGetLastError(), "test_sort launch");
+    return B200GS_OK;
+}
+size_t b200gs_test_sort_scratch_bytes(int64_t n) { return test_sort32_scratch_bytes(n); }
 
 int b200gs_test_exp(const float *x, float *y, int64_t n, void *stream)
 {

@@ -1,21 +1,21 @@
-// binning.cu -- F2..F5 re-designed around a DEPTH PRE-SORT.
+// binning.cu -- F2..F5 re-designed around a DEPTH PRE-SORT, all kernels hand-written.
 //
 // Upstream sorts D = sum(tiles_touched) 64-bit (tile|depth) keys: ~7 radix passes over every (Gaussian, tile)
 // instance.  The order it defines -- inside each tile ascending depth, ties by ascending Gaussian index -- is
 // reproduced here with far less traffic:
-//   1. sort the V*P Gaussians once by (view, depth bits)      [stable; V*P is 4-5x smaller than D]
-//   2. inclusive scan of tiles_touched IN THAT ORDER           -> D and the emission offsets
+//   1. sort the V*P Gaussians once by (view, depth bits)   [stable LSD radix, 8-bit digits; V*P is 4-5x smaller than D]
+//   2. inclusive scan of tiles_touched IN THAT ORDER        [single-pass decoupled look-back] -> D and emission offsets
 //   3. emit instances in depth order: key = view*tiles + tile (32 bit), value = record index
-//   4. STABLE sort by the tile key only (12-18 bits: 2-3 passes over 8-byte pairs instead of 7 over 12-byte pairs)
+//   4. STABLE sort by the tile key only                     [9-bit digits: 2 passes for 12..18 bits, 8-byte pairs]
 //   5. tile ranges from the sorted tile keys
 // Stability of step 4 keeps step 1's (depth, index) order inside every tile, so point_list and ranges are
 // bit-identical to the reference's single 64-bit sort (tests compare them, and the reconstructed 64-bit keys,
-// against the oracle).  Round-1 note: the radix passes and the scan are CUB device primitives (library code);
-// key construction, emission and range identification are ours.
-#include <cub/cub.cuh>
-
+// against the oracle).  The sort and scan primitives are in radix.cuh (onesweep passes with look-back).
 #include "common.cuh"
 #include "kernels.h"
+#include "radix.cuh"
+
+using namespace gsradix;
 
 static int bits_for(uint64_t n)
 {
@@ -24,11 +24,17 @@ static int bits_for(uint64_t n)
     return b;
 }
 
-struct TilesInOrder {
-    const uint32_t *tiles;
-    __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t &vp) const { return tiles[vp]; }
-};
-typedef cub::TransformInputIterator<uint32_t, TilesInOrder, const uint32_t *> TilesIter;
+// sort configuration
+constexpr int D_BITS = 8, D_IPT = 8, D_TILE = THREADS * D_IPT;    // depth sort: u64 keys
+constexpr int T_BITS = 9, T_IPT = 12, T_TILE = THREADS * T_IPT;   // tile sort: u32 keys
+constexpr int MAXP = 5;
+constexpr int SCAN_TILE = THREADS * SCAN_IPT;
+
+static size_t sort_scratch_bytes(int64_t n, int tile, int bins, int max_passes)
+{
+    const size_t nblocks = (size_t)((n + tile - 1) / tile) + 1;
+    return gs_align((size_t)MAXP * bins * 4) + gs_align(64 * 4) + gs_align(nblocks * bins * 4) * max_passes;
+}
 
 BinLayout binning_layout(int64_t capacity, int ntiles_total, int64_t n_vp)
 {
@@ -44,35 +50,74 @@ BinLayout binning_layout(int64_t capacity, int ntiles_total, int64_t n_vp)
     L.dkeys_out = o; o += gs_align(nvp * 8);
     L.order_in = o; o += gs_align(nvp * 4);
     L.order = o; o += gs_align(nvp * 4);
-    size_t t1 = 0, t2 = 0, t3 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, t1, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr,
-                                    (uint32_t *)nullptr, (int64_t)cap, 0, 32);
-    cub::DeviceRadixSort::SortPairs(nullptr, t2, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const uint32_t *)nullptr,
-                                    (uint32_t *)nullptr, (int64_t)nvp, 0, 64);
-    TilesIter it((const uint32_t *)nullptr, TilesInOrder{nullptr});
-    cub::DeviceScan::InclusiveSum(nullptr, t3, it, (uint32_t *)nullptr, (int64_t)nvp);
-    size_t t = t1 > t2 ? t1 : t2;
-    t = t > t3 ? t : t3;
-    L.temp_bytes = gs_align(t) + 256;
+    const int tbits = bits_for((uint64_t)ntiles_total) > 0 ? bits_for((uint64_t)ntiles_total) : 1;
+    const size_t s_depth = sort_scratch_bytes((int64_t)nvp, D_TILE, 1 << D_BITS, MAXP);
+    const size_t s_tile = sort_scratch_bytes((int64_t)cap, T_TILE, 1 << T_BITS, (tbits + T_BITS - 1) / T_BITS);
+    const size_t s_scan = gs_align(((nvp + SCAN_TILE - 1) / SCAN_TILE + 1) * 8) + 256;
+    size_t t = s_depth > s_tile ? s_depth : s_tile;
+    t = t > s_scan ? t : s_scan;
+    L.temp_bytes = t;
     L.temp = o; o += L.temp_bytes;
     L.total = o;
     return L;
 }
 
-// depth pre-sort + scan in depth order.  dkeys_in / order_in were written by the preprocess kernel.
-int launch_depth_order(const uint32_t *tiles_touched, uint32_t *offsets_sorted, int64_t n_vp, int V, char *bin_base,
-                       const BinLayout &L, cudaStream_t st)
+// Generic driver: stable LSD radix sort of n pairs over key bits [0, nbits).  Buffers a/b ping-pong; on return
+// *keys_sorted / *vals_sorted point at whichever buffer holds the result.  scratch must be sort_scratch_bytes().
+template <typename KeyT, int RBITS, int IPT>
+static int radix_sort_pairs(KeyT *ka, KeyT *kb, uint32_t *va, uint32_t *vb, int64_t n, int nbits, char *scratch, size_t scratch_bytes,
+                            KeyT **keys_sorted, uint32_t **vals_sorted, cudaStream_t st, int *n_launches)
 {
-    size_t need = L.temp_bytes;
-    const int end_bit = 32 + bits_for((uint64_t)V);
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(bin_base + L.temp, need, (const uint64_t *)(bin_base + L.dkeys_in),
-                                                    (uint64_t *)(bin_base + L.dkeys_out), (const uint32_t *)(bin_base + L.order_in),
-                                                    (uint32_t *)(bin_base + L.order), n_vp, 0, end_bit, st);
-    if (e != cudaSuccess) return -1;
-    TilesIter it((const uint32_t *)(bin_base + L.order), TilesInOrder{tiles_touched});
-    need = L.temp_bytes;
-    e = cub::DeviceScan::InclusiveSum(bin_base + L.temp, need, it, offsets_sorted, n_vp, st);
-    return e == cudaSuccess ? 0 : -2;
+    constexpr int BINS = 1 << RBITS, TILE = THREADS * IPT;
+    if (nbits < 1) nbits = 1;
+    const int npass = (nbits + RBITS - 1) / RBITS;
+    if (npass > MAXP) return -1;
+    const int last_bits = nbits - (npass - 1) * RBITS;
+    const size_t nblocks = (size_t)((n + TILE - 1) / TILE);
+    uint32_t *hist = (uint32_t *)scratch;
+    uint32_t *tickets = (uint32_t *)(scratch + gs_align((size_t)MAXP * BINS * 4));
+    char *status0 = scratch + gs_align((size_t)MAXP * BINS * 4) + gs_align(64 * 4);
+    const size_t status_stride = gs_align((nblocks + 1) * BINS * 4);
+    const size_t used = (size_t)(status0 - scratch) + status_stride * npass;
+    if (used > scratch_bytes) return -2;
+    cudaMemsetAsync(scratch, 0, used, st);
+    const int hgrid = (int)min((size_t)148 * 8, (size_t)((n + THREADS - 1) / THREADS));
+    histogram_kernel<KeyT, RBITS, MAXP><<<hgrid, THREADS, 0, st>>>(ka, n, npass, 0, last_bits, hist);
+    scan_hist_kernel<RBITS><<<npass, THREADS, 0, st>>>(hist);
+    KeyT *kin = ka, *kout = kb;
+    uint32_t *vin = va, *vout = vb;
+    for (int p = 0; p < npass; p++) {
+        const int bits = (p == npass - 1) ? last_bits : RBITS;
+        onesweep_kernel<KeyT, RBITS, IPT><<<(unsigned)nblocks, THREADS, 0, st>>>(
+            kin, kout, vin, vout, n, p * RBITS, bits, hist + (size_t)p * BINS, (volatile uint32_t *)(status0 + status_stride * p), tickets + p);
+        KeyT *tk = kin; kin = kout; kout = tk;
+        uint32_t *tv = vin; vin = vout; vout = tv;
+    }
+    *keys_sorted = kin;
+    *vals_sorted = vin;
+    *n_launches += 2 + npass;
+    return 0;
+}
+
+// depth pre-sort + scan in depth order.  dkeys_in / order_in were written by the preprocess kernel.
+// On return *order_sorted points at the sorted record indices (inside bin_base).
+int launch_depth_order(const uint32_t *tiles_touched, uint32_t *offsets_sorted, int64_t n_vp, int V, char *bin_base,
+                       const BinLayout &L, const uint32_t **order_sorted, cudaStream_t st, int *n_launches)
+{
+    uint64_t *ks = nullptr;
+    uint32_t *vs = nullptr;
+    if (radix_sort_pairs<uint64_t, D_BITS, D_IPT>((uint64_t *)(bin_base + L.dkeys_in), (uint64_t *)(bin_base + L.dkeys_out),
+                                                  (uint32_t *)(bin_base + L.order_in), (uint32_t *)(bin_base + L.order), n_vp,
+                                                  32 + bits_for((uint64_t)V), bin_base + L.temp, L.temp_bytes, &ks, &vs, st, n_launches))
+        return -1;
+    *order_sorted = vs;
+    const size_t nblocks = (size_t)((n_vp + SCAN_TILE - 1) / SCAN_TILE);
+    char *scr = bin_base + L.temp;
+    cudaMemsetAsync(scr, 0, gs_align((nblocks + 1) * 8) + 256, st);
+    scan_tiles_kernel<<<(unsigned)nblocks, THREADS, 0, st>>>(vs, tiles_touched, offsets_sorted, n_vp, (volatile uint64_t *)(scr + 256),
+                                                            (uint32_t *)scr);
+    *n_launches += 1;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 // one thread per Gaussian IN DEPTH ORDER: writes its tile keys at the offsets the scan assigned
@@ -113,8 +158,10 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t *__rest
     if (j == D - 1) ranges[t].y = (uint32_t)D;
 }
 
-int launch_binning(const uint2 *rects, const uint32_t *offsets_sorted, int P, int V, int grid_x, int grid_y, int64_t D,
-                   char *bin_base, const BinLayout &L, cudaStream_t st, int *n_launches)
+// After this call the sorted tile keys are at bin_base+L.keys_out and the point list at bin_base+L.vals_out
+// (a device-to-device copy fixes the parity when the number of passes is even).
+int launch_binning(const uint32_t *order_sorted, const uint2 *rects, const uint32_t *offsets_sorted, int P, int V, int grid_x, int grid_y,
+                   int64_t D, char *bin_base, const BinLayout &L, cudaStream_t st, int *n_launches)
 {
     const int ntiles = grid_x * grid_y;
     const int64_t n_vp = (int64_t)P * V;
@@ -123,14 +170,29 @@ int launch_binning(const uint2 *rects, const uint32_t *offsets_sorted, int P, in
     uint2 *ranges = (uint2 *)(bin_base + L.ranges);
     cudaMemsetAsync(ranges, 0, (size_t)ntiles * V * 8, st);
     if (D == 0) return 0;
-    emit_tiles_kernel<<<(unsigned)((n_vp + 255) / 256), 256, 0, st>>>((const uint32_t *)(bin_base + L.order), rects, offsets_sorted, P,
-                                                                      n_vp, grid_x, ntiles, keys_in, vals_in);
-    size_t need = L.temp_bytes;
-    const int end_bit = bits_for((uint64_t)ntiles * V);
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(bin_base + L.temp, need, keys_in, keys_out, vals_in, vals_out, D, 0,
-                                                    end_bit > 0 ? end_bit : 1, st);
-    if (e != cudaSuccess) return -2;
+    if (D >= ((int64_t)1 << 30)) return -3; // look-back status words carry 30-bit counts
+    const int nbits = bits_for((uint64_t)ntiles * V) > 0 ? bits_for((uint64_t)ntiles * V) : 1;
+    const int npass = (nbits + T_BITS - 1) / T_BITS;
+    // emit into the buffer from which `npass` ping-pong passes end in keys_out/vals_out
+    uint32_t *k0 = (npass & 1) ? keys_in : keys_out, *k1 = (npass & 1) ? keys_out : keys_in;
+    uint32_t *v0 = (npass & 1) ? vals_in : vals_out, *v1 = (npass & 1) ? vals_out : vals_in;
+    emit_tiles_kernel<<<(unsigned)((n_vp + 255) / 256), 256, 0, st>>>(order_sorted, rects, offsets_sorted, P, n_vp, grid_x, ntiles, k0, v0);
+    uint32_t *ks = nullptr, *vs = nullptr;
+    if (radix_sort_pairs<uint32_t, T_BITS, T_IPT>(k0, k1, v0, v1, D, nbits, bin_base + L.temp, L.temp_bytes, &ks, &vs, st, n_launches)) return -2;
+    if (ks != keys_out || vs != vals_out) return -4;
     tile_ranges_kernel<<<(unsigned)((D + 255) / 256), 256, 0, st>>>(keys_out, D, ranges);
     *n_launches += 2;
     return 0;
 }
+
+// test hook: sort n (u32 key, u32 value) pairs stably over the low nbits of the key with the tile-sort kernels
+int launch_test_sort32(uint32_t *ka, uint32_t *kb, uint32_t *va, uint32_t *vb, int64_t n, int nbits, char *scratch, size_t scratch_bytes,
+                       int *result_in_b, cudaStream_t st)
+{
+    uint32_t *ks = nullptr, *vs = nullptr;
+    int nl = 0;
+    const int rc = radix_sort_pairs<uint32_t, T_BITS, T_IPT>(ka, kb, va, vb, n, nbits, scratch, scratch_bytes, &ks, &vs, st, &nl);
+    *result_in_b = (ks == kb);
+    return rc;
+}
+size_t test_sort32_scratch_bytes(int64_t n) { return sort_scratch_bytes(n, T_TILE, 1 << T_BITS, 4); }

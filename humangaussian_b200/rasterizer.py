@@ -48,7 +48,8 @@ class _StateView(C.Structure):
 _lib = None
 EXPORTS = ["b200gs_forward", "b200gs_backward", "b200gs_mark_visible", "b200gs_describe_state", "b200gs_test_exp",
            "b200gs_geom_bytes", "b200gs_image_bytes", "b200gs_binning_bytes", "b200gs_backward_scratch_bytes",
-           "b200gs_last_cuda_error", "b200gs_abi_version", "b200gs_launch_count", "b200gs_profile_enable", "b200gs_profile_read"]
+           "b200gs_last_cuda_error", "b200gs_abi_version", "b200gs_launch_count", "b200gs_profile_enable", "b200gs_profile_read",
+           "b200gs_test_sort_pairs", "b200gs_test_sort_scratch_bytes"]
 STAGES = ["preprocess_fwd", "scan", "binning", "blend_fwd", "blend_bwd", "preprocess_bwd"]
 
 
@@ -79,6 +80,9 @@ def load_library():
     L.b200gs_describe_state.argtypes = [C.POINTER(_Params), vp, vp, i64, vp, C.POINTER(_StateView)]
     L.b200gs_test_exp.restype = C.c_int
     L.b200gs_test_exp.argtypes = [vp, vp, i64, vp]
+    L.b200gs_test_sort_pairs.restype = C.c_int
+    L.b200gs_test_sort_pairs.argtypes = [vp, vp, vp, vp, i64, i32, vp, sz, C.POINTER(i32), vp]
+    L.b200gs_test_sort_scratch_bytes.restype = sz; L.b200gs_test_sort_scratch_bytes.argtypes = [i64]
     L.b200gs_last_cuda_error.restype = C.c_char_p
     L.b200gs_launch_count.restype = i64
     L.b200gs_profile_enable.restype = None; L.b200gs_profile_enable.argtypes = [C.c_int]
@@ -394,6 +398,20 @@ def forward_with_state(**kw):
     pl = state["point_list"].to(torch.int64) & 0xFFFFFFFF
     state["sorted_keys"] = ((state["sorted_tile_keys"].to(torch.int64) & 0xFFFFFFFF) << 32) | dbits[pl]
     return color, radii, depth, alpha, state, st
+
+
+def device_sort_pairs(keys: torch.Tensor, vals: torch.Tensor, nbits: int):
+    """The binning stage's stable radix sort (int32 tensors reinterpreted as u32), exposed for tests."""
+    L = load_library()
+    ka, va = keys.contiguous().clone(), vals.contiguous().clone()
+    kb, vb = torch.empty_like(ka), torch.empty_like(va)
+    n = ka.numel()
+    scratch = torch.empty(L.b200gs_test_sort_scratch_bytes(n), dtype=torch.uint8, device=ka.device)
+    in_b = C.c_int32(0)
+    with torch.cuda.device(ka.device):
+        _check(L.b200gs_test_sort_pairs(_ptr(ka), _ptr(kb), _ptr(va), _ptr(vb), n, int(nbits), _ptr(scratch), scratch.numel(),
+                                        C.byref(in_b), _stream(ka.device)), "test_sort_pairs")
+    return (kb, vb) if in_b.value else (ka, va)
 
 
 def device_exp(x: torch.Tensor) -> torch.Tensor:

@@ -133,6 +133,12 @@ typedef struct b200gs_state_view {
 int b200gs_describe_state(const b200gs_params *prm, const void *geom_buf, const void *binning_buf,
                           int64_t instance_capacity, const void *image_buf, b200gs_state_view *out);
 
+/* The stable radix sort of the binning stage, exposed for tests: sorts n (u32 key, u32 value) pairs over the low
+ * `nbits` key bits; buffers a/b ping-pong, *result_in_b tells which holds the result. */
+int b200gs_test_sort_pairs(uint32_t *keys_a, uint32_t *keys_b, uint32_t *vals_a, uint32_t *vals_b, int64_t n, int32_t nbits,
+                           void *scratch, size_t scratch_bytes, int32_t *result_in_b, void *stream);
+size_t b200gs_test_sort_scratch_bytes(int64_t n);
+
 /* The deterministic exp used by the blend kernels, evaluated on the device for n floats (parity pin vs oracle). */
 int b200gs_test_exp(const float *x, float *y, int64_t n, void *stream);
 
