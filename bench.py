@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--gaussians", type=int, default=300000)
     ap.add_argument("--res", type=int, default=1024)
     ap.add_argument("--sh-degree", type=int, default=3)
+    ap.add_argument("--per-view", action="store_true",
+                    help="drive the rasteriser one view per call (the reference's calling pattern, GaussianDreamer.py:244-248) "
+                         "instead of one batched call per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--stage-json", default=None, help="also write the per-stage timing table to this file")
@@ -183,6 +186,7 @@ def workload_config(args, n):
     return {"workload": f"BASELINE configs[3]: synthetic body P={args.gaussians} SH deg {args.sh_degree}, {args.res}x{args.res}, "
                         f"{args.views} seeded orbit cameras per GPU, fwd+bwd (loss = sum of fixed N(0,1) weights on RGB, depth, alpha)",
             "gaussians": args.gaussians, "views_per_gpu": args.views, "resolution": args.res, "sh_degree": args.sh_degree,
+            "calling_pattern": "one rasteriser call per view" if getattr(args, "per_view", False) else "one batched call per step",
             "parallelism": f"views sharded over {n} GPU(s); scene broadcast once; packed-gradient all-reduce per step" if n > 1 else "single GPU",
             "l2_policy": "per-step working set (64 views x ~48 MB images/state + 0.9 GB geometry + sort buffers) >> 126 MB L2; no explicit flush"}
 
@@ -248,8 +252,14 @@ def run_b200(args):
             v_vm, v_pm, v_cp = cd[:16 * V].view(V, 4, 4), cd[16 * V:32 * V].view(V, 4, 4), cd[32 * V:].view(V, 3)
         xyz, sc, rot, op, sh = views_of(f)
         flat.grad = None
-        c, r, d, a = R.rasterize_views(means3D=xyz, opacities=op, viewmatrices=v_vm, projmatrices=v_pm, camposs=v_cp, tanfovx=tanx,
-                                       tanfovy=tany, image_height=HW, image_width=HW, bg=bg, sh_degree=deg, shs=sh, scales=sc, rotations=rot)
+        if args.per_view:  # V sequential single-view calls, outputs stacked (what the SDS loop does today)
+            outs = [R.rasterize_views(means3D=xyz, opacities=op, viewmatrices=v_vm[i:i + 1], projmatrices=v_pm[i:i + 1],
+                                      camposs=v_cp[i:i + 1], tanfovx=tanx[i:i + 1], tanfovy=tany[i:i + 1], image_height=HW,
+                                      image_width=HW, bg=bg, sh_degree=deg, shs=sh, scales=sc, rotations=rot) for i in range(V)]
+            c, r, d, a = (torch.cat([o[k] for o in outs], 0) for k in range(4))
+        else:
+            c, r, d, a = R.rasterize_views(means3D=xyz, opacities=op, viewmatrices=v_vm, projmatrices=v_pm, camposs=v_cp, tanfovx=tanx,
+                                           tanfovy=tany, image_height=HW, image_width=HW, bg=bg, sh_degree=deg, shs=sh, scales=sc, rotations=rot)
         if e2e:
             loss = (c * gw[0]).sum() + (d * gw[1]).sum() + (a * gw[2]).sum()
             loss.backward()
