@@ -1,45 +1,32 @@
 // blend.cu -- F6 forward alpha blend and B1 backward blend.
 //
-// One CTA per 16x16 tile (grid.y = view), 8 warps; each warp owns an 8x4 pixel patch.
-//   * Staging: 256 instances per batch, three 128-bit loads per thread (sorted id -> 48-byte GeomRec) into
-//     shared memory, plus an 8-bit patch mask from the Gaussian's conservative alpha-support box (hx, hy).
-//   * Per-warp compaction: every warp turns the masks into its own ordered list of the instances that can
-//     reach its patch (8 ballots per batch), so rejected (instance, patch) pairs cost nothing in the blend loop.
+// PATCH-PARALLEL: every warp owns one 8x4 pixel patch of a 16x16 tile and walks the tile's instance list ON ITS
+// OWN -- no CTA-wide barrier anywhere in the loops.  (The first version staged 256 instances per CTA between
+// __syncthreads; ncu showed 35 % of warp-time parked on that barrier because the eight patches of a tile see very
+// different numbers of Gaussians.)  CTAs are 64 threads = two independent warps (a 16x4 strip), so the block
+// scheduler balances patches dynamically and a finished warp frees its slot almost immediately.
+//   * Chunks of 32 list entries: lane l loads entry l's id and the first 16 bytes of its 48-byte GeomRec
+//     (px, py, hx, hy), tests the Gaussian's conservative alpha-support box against the warp's patch, and the
+//     warp ballots.  Hits load the rest of the record and are compacted, in order, into a per-warp shared-memory
+//     slab; the next chunk's id/box loads are already in flight while the hits are blended.
 //     Measured on the bench workload: 1.97 of 8 patches survive per instance, 14.3 of 32 lanes contribute.
 //   * Tile lists are exactly the reference's (tile/sort indices bit-identical); culling only skips pairs whose
 //     alpha is provably < 1/255, so images are unchanged.  Forward arithmetic follows the pinned order of
 //     common.cuh: images are bit-identical to the CPU oracle.
 //   * Backward: per-pixel terms are expressed as ten sums per Gaussian -- six sums of q = G*dL/dalpha
-//     (q, two mean-gradient forms, q dx^2, q dx dy, q dy^2) and four colour/depth weights -- reduced over the 32 lanes with a
-//     12-shuffle multi-value butterfly (not 10 x 5 shuffles), then ten lanes each issue one
+//     (q, two mean-gradient forms, q dx^2, q dx dy, q dy^2) and four colour/depth weights -- reduced over the
+//     32 lanes with a 12-shuffle multi-value butterfly (not 10 x 5 shuffles), then ten lanes each issue one
 //     red.global.add.f32 into the Gaussian's 48-byte ScreenGrad record.  Upstream: ~10 atomics per PIXEL.
 #include "common.cuh"
 #include "kernels.h"
 
-#define BATCH 256
 #define FULL 0xffffffffu
+#define WARPS_PER_CTA 2
 
-__device__ __forceinline__ uint32_t patch_mask(float px, float py, float hx, float hy, float tx0, float ty0)
+// does the support box [px-hx,px+hx] x [py-hy,py+hy] reach the patch [x0,x0+7] x [y0,y0+3] ?
+__device__ __forceinline__ bool box_hits_patch(const float4 g0, float x0, float y0)
 {
-    // bit (wy*2 + wx): patch columns [tx0+8wx, +7], rows [ty0+4wy, +3] may intersect [px-hx,px+hx]x[py-hy,py+hy]
-    if (hx < 0.0f) return 0u; // 255*opacity <= 1: can never reach alpha >= 1/255
-    const float xl = px - hx, xh = px + hx, yl = py - hy, yh = py + hy;
-    uint32_t xm = 0, ym = 0;
-#pragma unroll
-    for (int wx = 0; wx < 2; wx++) {
-        const float a0 = tx0 + 8.0f * wx;
-        if (xh >= a0 && xl <= a0 + 7.0f) xm |= 1u << wx;
-    }
-#pragma unroll
-    for (int wy = 0; wy < 4; wy++) {
-        const float b0 = ty0 + 4.0f * wy;
-        if (yh >= b0 && yl <= b0 + 3.0f) ym |= 1u << wy;
-    }
-    uint32_t m = 0;
-#pragma unroll
-    for (int wy = 0; wy < 4; wy++)
-        if (ym & (1u << wy)) m |= xm << (2 * wy);
-    return m;
+    return (g0.z >= 0.0f) && (g0.x + g0.z >= x0) && (g0.x - g0.z <= x0 + 7.0f) && (g0.y + g0.w >= y0) && (g0.y - g0.w <= y0 + 3.0f);
 }
 
 // power with the conic pre-scaled at staging time (A' = -A/2, B' = -B, C' = -C/2: exact operations, so the
@@ -51,36 +38,34 @@ __device__ __forceinline__ float power_prescaled(float Ap, float Bp, float Cp, f
     return ffma(dx, u, w);
 }
 
-// Shared-memory tile of one batch: 256 staged records (48 B each, conic pre-scaled), their patch masks, and one
-// compacted index list per warp.  Accessed only through this struct so every access is a plain LDS/STS with an
-// immediate offset (no generic-address arithmetic in the inner loops).
-struct __align__(16) BatchSmem {
-    float4 rec[BATCH * 3];
-    uint32_t id[BATCH];
-    uint8_t mask[BATCH];
-    uint8_t list[8][BATCH];
+// per-warp slab of the (at most 32) hits of the current chunk
+struct __align__(16) WarpSlab {
+    float4 rec[32 * 3]; // px,py,hx,hy | A',B',C',o | r,g,b,depth
+    uint32_t pos[32];   // 1-based position in the tile list (forward) / 0-based (backward)
+    uint32_t id[32];    // record index (backward: address of the ScreenGrad accumulator)
 };
 
 // ------------------------------------------------------------------------------------------------
 // F6
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) blend_fwd_kernel(BlendArgs a)
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_fwd_kernel(BlendArgs a)
 {
-    __shared__ BatchSmem sm;
+    __shared__ WarpSlab slabs[WARPS_PER_CTA];
 
     const int ntiles = a.grid_x * a.grid_y;
-    const int tile = blockIdx.x, v = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x >> 2, band = blockIdx.x & 3, v = blockIdx.y;
     const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int px = tile_x * GS_TILE + (warp & 1) * 8 + (lane & 7);
-    const int py = tile_y * GS_TILE + (warp >> 1) * 4 + (lane >> 3);
+    const int x0 = tile_x * GS_TILE + warp * 8, y0 = tile_y * GS_TILE + band * 4;
+    const int px = x0 + (lane & 7), py = y0 + (lane >> 3);
     const bool inside = px < a.W && py < a.H;
-    const float fpx = (float)px, fpy = (float)py;
-    const float tx0 = (float)(tile_x * GS_TILE), ty0 = (float)(tile_y * GS_TILE);
+    const float fpx = (float)px, fpy = (float)py, fx0 = (float)x0, fy0 = (float)y0;
+    WarpSlab &sl = slabs[warp];
 
     const uint2 range = a.ranges[(size_t)v * ntiles + tile];
     const int n_total = (int)(range.y - range.x);
     const float4 *recs4 = reinterpret_cast<const float4 *>(a.recs);
+    const uint32_t *plist = a.point_list + range.x;
     const uint32_t lt = (1u << lane) - 1u;
 
     // T == 0 is the "done" sentinel: a finished (or out-of-image) pixel keeps failing the T test and never
@@ -89,36 +74,45 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendArgs a)
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, Dd = 0.f, Aa = 0.f;
     uint32_t last = 0;
 
-    for (int base = 0; base < n_total; base += BATCH) {
-        if (__syncthreads_count(T == 0.0f) == 256) break;
-        const int n = min(BATCH, n_total - base);
-        if (tid < n) {
-            const uint32_t id = __ldg(a.point_list + range.x + base + tid);
-            const float4 g0 = __ldg(recs4 + 3 * (size_t)id);
-            const float4 g1 = __ldg(recs4 + 3 * (size_t)id + 1);
-            sm.rec[3 * tid] = g0;
-            sm.rec[3 * tid + 1] = make_float4(fmul(-0.5f, g1.x), -g1.y, fmul(-0.5f, g1.z), g1.w);
-            sm.rec[3 * tid + 2] = __ldg(recs4 + 3 * (size_t)id + 2);
-            sm.mask[tid] = (uint8_t)patch_mask(g0.x, g0.y, g0.z, g0.w, tx0, ty0);
+    // software pipeline: the id / support box of chunk c+1 are loaded while chunk c is blended
+    uint32_t id_c = 0;
+    float4 g0_c = make_float4(0.f, 0.f, -1.f, -1.f);
+    if (lane < n_total) {
+        id_c = __ldg(plist + lane);
+        g0_c = __ldg(recs4 + 3 * (size_t)id_c);
+    }
+    for (int base = 0; base < n_total; base += 32) {
+        if (__all_sync(FULL, T == 0.0f)) break;
+        const bool hit = box_hits_patch(g0_c, fx0, fy0);
+        const uint32_t b = __ballot_sync(FULL, hit);
+        float4 g1, g2;
+        if (hit) {
+            g1 = __ldg(recs4 + 3 * (size_t)id_c + 1);
+            g2 = __ldg(recs4 + 3 * (size_t)id_c + 2);
         }
-        __syncthreads();
-        if (__all_sync(FULL, T == 0.0f)) continue;
-        int cnt = 0;
-        for (int k = 0; k < n; k += 32) {
-            const int j = k + lane;
-            const bool hit = (j < n) && ((sm.mask[j] >> warp) & 1);
-            const uint32_t b = __ballot_sync(FULL, hit);
-            if (hit) sm.list[warp][cnt + __popc(b & lt)] = (uint8_t)j;
-            cnt += __popc(b);
+        const float4 g0_h = g0_c;
+        const int e_n = base + 32 + lane;
+        g0_c = make_float4(0.f, 0.f, -1.f, -1.f);
+        if (e_n < n_total) {
+            id_c = __ldg(plist + e_n);
+            g0_c = __ldg(recs4 + 3 * (size_t)id_c);
+        }
+        if (b == 0u) continue;
+        if (hit) {
+            const int slot = __popc(b & lt);
+            sl.rec[3 * slot] = g0_h;
+            sl.rec[3 * slot + 1] = make_float4(fmul(-0.5f, g1.x), -g1.y, fmul(-0.5f, g1.z), g1.w);
+            sl.rec[3 * slot + 2] = g2;
+            sl.pos[slot] = (uint32_t)(base + lane + 1);
         }
         __syncwarp();
+        const int cnt = __popc(b);
         for (int i = 0; i < cnt; i++) {
-            const int j = sm.list[warp][i];
-            const float4 g0 = sm.rec[3 * j], g1 = sm.rec[3 * j + 1];
+            const float4 g0 = sl.rec[3 * i], q1 = sl.rec[3 * i + 1];
             const float dx = fsub(g0.x, fpx), dy = fsub(g0.y, fpy);
-            const float power = power_prescaled(g1.x, g1.y, g1.z, dx, dy);
+            const float power = power_prescaled(q1.x, q1.y, q1.z, dx, dy);
             if (!(power > 0.0f)) {
-                const float alpha = fminf(GS_ALPHA_MAX, fmul(g1.w, gs_exp(power)));
+                const float alpha = fminf(GS_ALPHA_MAX, fmul(q1.w, gs_exp(power)));
                 if (!(alpha < GS_ALPHA_MIN)) {
                     const float test_T = fmul(T, fsub(1.0f, alpha));
                     if (test_T < GS_T_MIN) {
@@ -126,17 +120,17 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendArgs a)
                         T = 0.0f;
                     } else {
                         const float w = fmul(alpha, T);
-                        const float4 g2 = sm.rec[3 * j + 2];
-                        C0 = ffma(g2.x, w, C0); C1 = ffma(g2.y, w, C1); C2 = ffma(g2.z, w, C2);
-                        Dd = ffma(g2.w, w, Dd);
+                        const float4 q2 = sl.rec[3 * i + 2];
+                        C0 = ffma(q2.x, w, C0); C1 = ffma(q2.y, w, C1); C2 = ffma(q2.z, w, C2);
+                        Dd = ffma(q2.w, w, Dd);
                         Aa = fadd(Aa, w);
                         T = test_T;
-                        last = (uint32_t)(base + j + 1);
+                        last = sl.pos[i];
                     }
                 }
             }
-            if (__all_sync(FULL, T == 0.0f)) break;
         }
+        __syncwarp();
     }
     if (inside) {
         if (T != 0.0f) T_out = T;
@@ -155,8 +149,8 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendArgs a)
 
 void launch_blend_fwd(const BlendArgs &a, cudaStream_t st)
 {
-    dim3 grid(a.grid_x * a.grid_y, a.V);
-    blend_fwd_kernel<<<grid, 256, 0, st>>>(a);
+    dim3 grid(a.grid_x * a.grid_y * 4, a.V);
+    blend_fwd_kernel<<<grid, 32 * WARPS_PER_CTA, 0, st>>>(a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -194,24 +188,25 @@ __device__ __forceinline__ int slot_of_lane(int lane)
     return (h16 ? 5 : 0) + (h8 ? 3 : 0) + (h4 ? 2 : 0) + (h2 ? 1 : 0);
 }
 
-__global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a)
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_bwd_kernel(BlendBwdArgs a)
 {
-    __shared__ BatchSmem sm;
-    __shared__ int s_max;
+    __shared__ WarpSlab slabs[WARPS_PER_CTA];
 
     const int ntiles = a.grid_x * a.grid_y;
-    const int tile = blockIdx.x, v = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x >> 2, band = blockIdx.x & 3, v = blockIdx.y;
     const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int px = tile_x * GS_TILE + (warp & 1) * 8 + (lane & 7);
-    const int py = tile_y * GS_TILE + (warp >> 1) * 4 + (lane >> 3);
+    const int x0 = tile_x * GS_TILE + warp * 8, y0 = tile_y * GS_TILE + band * 4;
+    const int px = x0 + (lane & 7), py = y0 + (lane >> 3);
     const bool inside = px < a.W && py < a.H;
-    const float fpx = (float)px, fpy = (float)py;
-    const float tx0 = (float)(tile_x * GS_TILE), ty0 = (float)(tile_y * GS_TILE);
+    const float fpx = (float)px, fpy = (float)py, fx0 = (float)x0, fy0 = (float)y0;
+    WarpSlab &sl = slabs[warp];
     const uint2 range = a.ranges[(size_t)v * ntiles + tile];
     const float4 *recs4 = reinterpret_cast<const float4 *>(a.recs);
+    const uint32_t *plist = a.point_list + range.x;
     const size_t HW = (size_t)a.H * a.W;
     const size_t pix = (size_t)py * a.W + px;
+    const uint32_t lt = (1u << lane) - 1u;
 
     float T_final = 1.f, gC0 = 0.f, gC1 = 0.f, gC2 = 0.f, gD = 0.f, gA = 0.f;
     int last = 0;
@@ -225,17 +220,13 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a)
         if (a.dL_ddepth) gD = a.dL_ddepth[v * HW + pix];
         if (a.dL_dalpha) gA = a.dL_dalpha[v * HW + pix];
     }
-    if (tid == 0) s_max = 0;
-    __syncthreads();
-    int wmax = last; // per-warp maximum: entries at or beyond it cannot contribute in this warp
+    int wmax = last; // list positions at or beyond the patch's largest n_contrib cannot contribute here
     wmax = max(wmax, __shfl_xor_sync(FULL, wmax, 16));
     wmax = max(wmax, __shfl_xor_sync(FULL, wmax, 8));
     wmax = max(wmax, __shfl_xor_sync(FULL, wmax, 4));
     wmax = max(wmax, __shfl_xor_sync(FULL, wmax, 2));
     wmax = max(wmax, __shfl_xor_sync(FULL, wmax, 1));
-    if (lane == 0) atomicMax(&s_max, wmax);
-    __syncthreads();
-    const int n_total = s_max; // entries [0, n_total) of the tile list can have contributed
+    if (wmax == 0) return;
 
     const float bg_dot = a.bg[0] * gC0 + a.bg[1] * gC1 + a.bg[2] * gC2;
     const int slot = slot_of_lane(lane);
@@ -243,61 +234,65 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a)
     float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, ld = 0.f;
     float ac0 = 0.f, ac1 = 0.f, ac2 = 0.f, ad = 0.f, aa = 0.f;
 
-    for (int hi = n_total; hi > 0; hi -= BATCH) {
-        const int n = min(BATCH, hi);
-        __syncthreads();
-        if (tid < n) {
-            const uint32_t id = __ldg(a.point_list + range.x + (hi - 1 - tid));
-            const float4 g0 = __ldg(recs4 + 3 * (size_t)id);
-            const float4 g1 = __ldg(recs4 + 3 * (size_t)id + 1);
-            sm.rec[3 * tid] = g0;
-            sm.rec[3 * tid + 1] = make_float4(fmul(-0.5f, g1.x), -g1.y, fmul(-0.5f, g1.z), g1.w);
-            sm.rec[3 * tid + 2] = __ldg(recs4 + 3 * (size_t)id + 2);
-            sm.id[tid] = id;
-            sm.mask[tid] = (uint8_t)patch_mask(g0.x, g0.y, g0.z, g0.w, tx0, ty0);
+    // back to front: chunk [hi-32, hi), lane l <-> list position hi-1-l; the next chunk's loads are in flight
+    uint32_t id_c = 0;
+    float4 g0_c = make_float4(0.f, 0.f, -1.f, -1.f);
+    if (wmax - 1 - lane >= 0) {
+        id_c = __ldg(plist + (wmax - 1 - lane));
+        g0_c = __ldg(recs4 + 3 * (size_t)id_c);
+    }
+    for (int hi = wmax; hi > 0; hi -= 32) {
+        const bool hit = box_hits_patch(g0_c, fx0, fy0);
+        const uint32_t b = __ballot_sync(FULL, hit);
+        float4 g1, g2;
+        if (hit) {
+            g1 = __ldg(recs4 + 3 * (size_t)id_c + 1);
+            g2 = __ldg(recs4 + 3 * (size_t)id_c + 2);
         }
-        __syncthreads();
-        // batch entry j sits at list position hi-1-j; it can matter to this warp only if hi-1-j < wmax
-        const int first = max(0, hi - wmax);
-        if (first >= n) continue;
-        int cnt = 0;
-        {
-            const uint32_t lt = (1u << lane) - 1u;
-            for (int k = first & ~31; k < n; k += 32) {
-                const int j = k + lane;
-                const bool hit = (j < n) && (j >= first) && ((sm.mask[j] >> warp) & 1);
-                const uint32_t b = __ballot_sync(FULL, hit);
-                if (hit) sm.list[warp][cnt + __popc(b & lt)] = (uint8_t)j;
-                cnt += __popc(b);
-            }
-            __syncwarp();
+        const float4 g0_h = g0_c;
+        const uint32_t id_h = id_c;
+        const int p_n = hi - 32 - 1 - lane;
+        g0_c = make_float4(0.f, 0.f, -1.f, -1.f);
+        if (p_n >= 0) {
+            id_c = __ldg(plist + p_n);
+            g0_c = __ldg(recs4 + 3 * (size_t)id_c);
         }
+        if (b == 0u) continue;
+        if (hit) {
+            const int s = __popc(b & lt);
+            sl.rec[3 * s] = g0_h;
+            sl.rec[3 * s + 1] = make_float4(fmul(-0.5f, g1.x), -g1.y, fmul(-0.5f, g1.z), g1.w);
+            sl.rec[3 * s + 2] = g2;
+            sl.pos[s] = (uint32_t)(hi - 1 - lane);
+            sl.id[s] = id_h;
+        }
+        __syncwarp();
+        const int cnt = __popc(b);
         for (int i = 0; i < cnt; i++) {
-            const int j = sm.list[warp][i];
-            const int pos = hi - 1 - j; // 0-based position in the tile list
-            const float4 g0 = sm.rec[3 * j], g1 = sm.rec[3 * j + 1];
+            const int pos = (int)sl.pos[i]; // 0-based position in the tile list
+            const float4 g0 = sl.rec[3 * i], q1 = sl.rec[3 * i + 1];
             const float dx = fsub(g0.x, fpx), dy = fsub(g0.y, fpy);
-            const float power = power_prescaled(g1.x, g1.y, g1.z, dx, dy);
+            const float power = power_prescaled(q1.x, q1.y, q1.z, dx, dy);
             const float G = gs_exp(power);
-            const float alpha = fminf(GS_ALPHA_MAX, fmul(g1.w, G));
+            const float alpha = fminf(GS_ALPHA_MAX, fmul(q1.w, G));
             const bool contrib = (pos < last) && !(power > 0.0f) && !(alpha < GS_ALPHA_MIN);
             if (!__any_sync(FULL, contrib)) continue;
             float q = 0.f, w = 0.f;
             if (contrib) {
-                const float4 g2 = sm.rec[3 * j + 2];
+                const float4 q2 = sl.rec[3 * i + 2];
                 const float one_m_a = 1.0f - alpha;
                 const float inv = __frcp_rn(one_m_a);
                 T = T * inv;
                 w = alpha * T;
-                ac0 = fmaf(last_alpha, lc0 - ac0, ac0); lc0 = g2.x;
-                ac1 = fmaf(last_alpha, lc1 - ac1, ac1); lc1 = g2.y;
-                ac2 = fmaf(last_alpha, lc2 - ac2, ac2); lc2 = g2.z;
-                ad = fmaf(last_alpha, ld - ad, ad); ld = g2.w;
+                ac0 = fmaf(last_alpha, lc0 - ac0, ac0); lc0 = q2.x;
+                ac1 = fmaf(last_alpha, lc1 - ac1, ac1); lc1 = q2.y;
+                ac2 = fmaf(last_alpha, lc2 - ac2, ac2); lc2 = q2.z;
+                ad = fmaf(last_alpha, ld - ad, ad); ld = q2.w;
                 aa = fmaf(last_alpha, 1.0f - aa, aa);
-                float dL_dalpha = (g2.x - ac0) * gC0;
-                dL_dalpha = fmaf(g2.y - ac1, gC1, dL_dalpha);
-                dL_dalpha = fmaf(g2.z - ac2, gC2, dL_dalpha);
-                dL_dalpha = fmaf(g2.w - ad, gD, dL_dalpha);
+                float dL_dalpha = (q2.x - ac0) * gC0;
+                dL_dalpha = fmaf(q2.y - ac1, gC1, dL_dalpha);
+                dL_dalpha = fmaf(q2.z - ac2, gC2, dL_dalpha);
+                dL_dalpha = fmaf(q2.w - ad, gD, dL_dalpha);
                 dL_dalpha = fmaf(1.0f - aa, gA, dL_dalpha);
                 dL_dalpha *= T;
                 last_alpha = alpha;
@@ -307,18 +302,19 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a)
             // Mx = -sum q (A dx + B dy), My = -sum q (C dy + B dx): formed per pixel (not from the moments sum q dx,
             // sum q dy) so that the A.Sx + B.Sy cancellation of elongated Gaussians is not amplified by rounding.
             const float qx = q * dx, qy = q * dy;
-            const float mx = q * fmaf(g1.y, dy, (g1.x + g1.x) * dx);
-            const float my = q * fmaf(g1.y, dx, (g1.z + g1.z) * dy);
+            const float mx = q * fmaf(q1.y, dy, (q1.x + q1.x) * dx);
+            const float my = q * fmaf(q1.y, dx, (q1.z + q1.z) * dy);
             const float e = butterfly10(q, mx, my, qx * dx, qx * dy, qy * dy, w * gC0, w * gC1, w * gC2, w * gD, lane);
-            if (slot >= 0) atomicAdd(reinterpret_cast<float *>(a.sgrad + sm.id[j]) + slot, e);
+            if (slot >= 0) atomicAdd(reinterpret_cast<float *>(a.sgrad + sl.id[i]) + slot, e);
         }
+        __syncwarp();
     }
 }
 
 void launch_blend_bwd(const BlendBwdArgs &a, cudaStream_t st)
 {
-    dim3 grid(a.grid_x * a.grid_y, a.V);
-    blend_bwd_kernel<<<grid, 256, 0, st>>>(a);
+    dim3 grid(a.grid_x * a.grid_y * 4, a.V);
+    blend_bwd_kernel<<<grid, 32 * WARPS_PER_CTA, 0, st>>>(a);
 }
 
 // ScreenGrad holds sums of q = G*dL/dalpha here: S0 = sum q, Mx = -sum q(A dx + B dy), My = -sum q(C dy + B dx),
