@@ -21,7 +21,13 @@
 #include "kernels.h"
 
 #define FULL 0xffffffffu
-#define WARPS_PER_CTA 2
+#ifndef WARPS_PER_CTA
+#define WARPS_PER_CTA 2 // independent patches per CTA (1, 2, 4 or 8); swept on B200: 2 is best by ~2 %
+#endif
+#ifndef BWD_MIN_BLOCKS
+#define BWD_MIN_BLOCKS 16 // caps the backward kernel at 64 registers (32 warps/SM)
+#endif
+#define CTAS_PER_TILE (8 / WARPS_PER_CTA)
 
 // does the support box [px-hx,px+hx] x [py-hy,py+hy] reach the patch [x0,x0+7] x [y0,y0+3] ?
 __device__ __forceinline__ bool box_hits_patch(const float4 g0, float x0, float y0)
@@ -54,9 +60,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_fwd_kernel(BlendArgs
 
     const int ntiles = a.grid_x * a.grid_y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x >> 2, band = blockIdx.x & 3, v = blockIdx.y;
+    const int tile = blockIdx.x / CTAS_PER_TILE, v = blockIdx.y;
+    const int patch = (blockIdx.x % CTAS_PER_TILE) * WARPS_PER_CTA + warp; // 0..7: bit0 = x half, bits 1-2 = row band
     const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
-    const int x0 = tile_x * GS_TILE + warp * 8, y0 = tile_y * GS_TILE + band * 4;
+    const int x0 = tile_x * GS_TILE + (patch & 1) * 8, y0 = tile_y * GS_TILE + (patch >> 1) * 4;
     const int px = x0 + (lane & 7), py = y0 + (lane >> 3);
     const bool inside = px < a.W && py < a.H;
     const float fpx = (float)px, fpy = (float)py, fx0 = (float)x0, fy0 = (float)y0;
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_fwd_kernel(BlendArgs
 
 void launch_blend_fwd(const BlendArgs &a, cudaStream_t st)
 {
-    dim3 grid(a.grid_x * a.grid_y * 4, a.V);
+    dim3 grid(a.grid_x * a.grid_y * CTAS_PER_TILE, a.V);
     blend_fwd_kernel<<<grid, 32 * WARPS_PER_CTA, 0, st>>>(a);
 }
 
@@ -188,15 +195,16 @@ __device__ __forceinline__ int slot_of_lane(int lane)
     return (h16 ? 5 : 0) + (h8 ? 3 : 0) + (h4 ? 2 : 0) + (h2 ? 1 : 0);
 }
 
-__global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_bwd_kernel(BlendBwdArgs a)
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_kernel(BlendBwdArgs a)
 {
     __shared__ WarpSlab slabs[WARPS_PER_CTA];
 
     const int ntiles = a.grid_x * a.grid_y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x >> 2, band = blockIdx.x & 3, v = blockIdx.y;
+    const int tile = blockIdx.x / CTAS_PER_TILE, v = blockIdx.y;
+    const int patch = (blockIdx.x % CTAS_PER_TILE) * WARPS_PER_CTA + warp; // 0..7: bit0 = x half, bits 1-2 = row band
     const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
-    const int x0 = tile_x * GS_TILE + warp * 8, y0 = tile_y * GS_TILE + band * 4;
+    const int x0 = tile_x * GS_TILE + (patch & 1) * 8, y0 = tile_y * GS_TILE + (patch >> 1) * 4;
     const int px = x0 + (lane & 7), py = y0 + (lane >> 3);
     const bool inside = px < a.W && py < a.H;
     const float fpx = (float)px, fpy = (float)py, fx0 = (float)x0, fy0 = (float)y0;
@@ -313,7 +321,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_bwd_kernel(BlendBwdA
 
 void launch_blend_bwd(const BlendBwdArgs &a, cudaStream_t st)
 {
-    dim3 grid(a.grid_x * a.grid_y * 4, a.V);
+    dim3 grid(a.grid_x * a.grid_y * CTAS_PER_TILE, a.V);
     blend_bwd_kernel<<<grid, 32 * WARPS_PER_CTA, 0, st>>>(a);
 }
 
