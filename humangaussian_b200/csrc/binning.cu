@@ -32,8 +32,9 @@ constexpr int SCAN_TILE = THREADS * SCAN_IPT;
 
 static size_t sort_scratch_bytes(int64_t n, int tile, int bins, int max_passes)
 {
+    (void)max_passes;
     const size_t nblocks = (size_t)((n + tile - 1) / tile) + 1;
-    return gs_align((size_t)MAXP * bins * 4) + gs_align(64 * 4) + gs_align(nblocks * bins * 4) * max_passes;
+    return gs_align((size_t)bins * 4) + gs_align(nblocks * bins * 4);
 }
 
 BinLayout binning_layout(int64_t capacity, int ntiles_total, int64_t n_vp)
@@ -73,29 +74,23 @@ static int radix_sort_pairs(KeyT *ka, KeyT *kb, uint32_t *va, uint32_t *vb, int6
     const int npass = (nbits + RBITS - 1) / RBITS;
     if (npass > MAXP) return -1;
     const int last_bits = nbits - (npass - 1) * RBITS;
-    const size_t nblocks = (size_t)((n + TILE - 1) / TILE);
-    uint32_t *hist = (uint32_t *)scratch;
-    uint32_t *tickets = (uint32_t *)(scratch + gs_align((size_t)MAXP * BINS * 4));
-    char *status0 = scratch + gs_align((size_t)MAXP * BINS * 4) + gs_align(64 * 4);
-    const size_t status_stride = gs_align((nblocks + 1) * BINS * 4);
-    const size_t used = (size_t)(status0 - scratch) + status_stride * npass;
-    if (used > scratch_bytes) return -2;
-    cudaMemsetAsync(scratch, 0, used, st);
-    const int hgrid = (int)min((size_t)148 * 8, (size_t)((n + THREADS - 1) / THREADS));
-    histogram_kernel<KeyT, RBITS, MAXP><<<hgrid, THREADS, 0, st>>>(ka, n, npass, 0, last_bits, hist);
-    scan_hist_kernel<RBITS><<<npass, THREADS, 0, st>>>(hist);
+    const uint32_t nblocks = (uint32_t)((n + TILE - 1) / TILE);
+    uint32_t *totals = (uint32_t *)scratch;
+    uint32_t *counts = (uint32_t *)(scratch + gs_align((size_t)BINS * 4));
+    if (gs_align((size_t)BINS * 4) + (size_t)nblocks * BINS * 4 > scratch_bytes) return -2;
     KeyT *kin = ka, *kout = kb;
     uint32_t *vin = va, *vout = vb;
     for (int p = 0; p < npass; p++) {
         const int bits = (p == npass - 1) ? last_bits : RBITS;
-        onesweep_kernel<KeyT, RBITS, IPT><<<(unsigned)nblocks, THREADS, 0, st>>>(
-            kin, kout, vin, vout, n, p * RBITS, bits, hist + (size_t)p * BINS, (volatile uint32_t *)(status0 + status_stride * p), tickets + p);
+        count_kernel<KeyT, RBITS, IPT><<<nblocks, THREADS, 0, st>>>(kin, n, p * RBITS, bits, counts, nblocks);
+        scan_counts_kernel<<<BINS, THREADS, 0, st>>>(counts, nblocks, totals);
+        scatter_kernel<KeyT, RBITS, IPT><<<nblocks, THREADS, 0, st>>>(kin, kout, vin, vout, n, p * RBITS, bits, counts, nblocks, totals);
         KeyT *tk = kin; kin = kout; kout = tk;
         uint32_t *tv = vin; vin = vout; vout = tv;
     }
     *keys_sorted = kin;
     *vals_sorted = vin;
-    *n_launches += 2 + npass;
+    *n_launches += 3 * npass;
     return 0;
 }
 

@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
 
     const float bg_dot = a.bg[0] * gC0 + a.bg[1] * gC1 + a.bg[2] * gC2;
     const int slot = slot_of_lane(lane);
+    float *const sg_slot = reinterpret_cast<float *>(a.sgrad) + (slot >= 0 ? slot : 0); // this lane's column of ScreenGrad
     float T = T_final;
     float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, ld = 0.f;
     float ac0 = 0.f, ac1 = 0.f, ac2 = 0.f, ad = 0.f, aa = 0.f;
@@ -289,7 +290,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
             if (contrib) {
                 const float4 q2 = sl.rec[3 * i + 2];
                 const float one_m_a = 1.0f - alpha;
-                const float inv = __frcp_rn(one_m_a);
+                float inv; // 1/(1-alpha), 1-alpha in [0.01, 1): the single-instruction MUFU reciprocal (<= 1 ulp) suffices
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(one_m_a));
                 T = T * inv;
                 w = alpha * T;
                 ac0 = fmaf(last_alpha, lc0 - ac0, ac0); lc0 = q2.x;
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
             const float mx = q * fmaf(q1.y, dy, (q1.x + q1.x) * dx);
             const float my = q * fmaf(q1.y, dx, (q1.z + q1.z) * dy);
             const float e = butterfly10(q, mx, my, qx * dx, qx * dy, qy * dy, w * gC0, w * gC1, w * gC2, w * gD, lane);
-            if (slot >= 0) atomicAdd(reinterpret_cast<float *>(a.sgrad + sl.id[i]) + slot, e);
+            if (slot >= 0) atomicAdd(sg_slot + 12 * (size_t)sl.id[i], e);
         }
         __syncwarp();
     }

@@ -1,16 +1,12 @@
 // radix.cuh -- hand-written stable LSD radix sort of (key, u32 value) pairs and a decoupled-look-back scan,
 // the two primitives of the binning stage.  sm_100a, 256-thread CTAs.
 //
-// One pass = ONE kernel ("onesweep"): every CTA takes a ticket (so CTAs are processed in launch-independent
-// order), ranks its tile of 256*IPT items by digit with warp match.any + per-warp shared counters (stable:
-// items keep their input order inside a digit), publishes its per-digit counts, resolves the exclusive prefix
-// over all earlier CTAs by decoupled look-back, reorders the tile through shared memory so that the final
-// global stores are contiguous runs per digit, and scatters.  The global per-digit bases of ALL passes come
-// from one up-front histogram kernel.  Digit width is a template parameter (6..9 bits): the tile-key sort of a
-// 64-view batch (18 bits) takes 2 passes of 9 bits where an 8-bit library sort takes 3.
-//
-// Memory per item and pass: one read + one write of (key, value) -- the single-pass lower bound used as the
-// "algorithmic bytes" of the sort in bench.py.
+// One pass = count (per-CTA digit histogram) -> scan over CTAs -> ranked scatter: every CTA ranks its tile of
+// 256*IPT items by digit with warp match.any + per-warp shared counters (stable: items keep their input order
+// inside a digit), reorders the tile through shared memory so that the final global stores are contiguous runs
+// per digit, and scatters to destinations taken from the scanned counts.  Digit width is a template parameter
+// (6..9 bits): the tile-key sort of a 64-view batch (18 bits) takes 2 passes of 9 bits where an 8-bit library
+// sort takes 3.  The scan over tiles_touched uses a decoupled look-back (one word per CTA, short walks).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,58 +23,74 @@ __device__ __forceinline__ uint32_t digit_of(KeyT k, int shift, int bits)
     return (uint32_t)(k >> shift) & ((1u << bits) - 1u);
 }
 
-// ---- histogram of up to MAXP digit positions in one read of the keys -----------------------------------------
-template <typename KeyT, int RADIX_BITS, int MAXP>
-__global__ void __launch_bounds__(THREADS) histogram_kernel(const KeyT *__restrict__ keys, int64_t n, int npass, int first_shift,
-                                                             int last_bits, uint32_t *__restrict__ hist /* [npass][BINS] */)
-{
-    constexpr int BINS = 1 << RADIX_BITS;
-    __shared__ uint32_t sh[MAXP * BINS];
-    for (int i = threadIdx.x; i < npass * BINS; i += THREADS) sh[i] = 0;
-    __syncthreads();
-    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
-        const KeyT k = keys[i];
-#pragma unroll
-        for (int p = 0; p < MAXP; p++)
-            if (p < npass) {
-                const int bits = (p == npass - 1) ? last_bits : RADIX_BITS;
-                atomicAdd(&sh[p * BINS + digit_of(k, first_shift + p * RADIX_BITS, bits)], 1u);
-            }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < npass * BINS; i += THREADS)
-        if (sh[i]) atomicAdd(&hist[i], sh[i]);
-}
+// ---- pass = three kernels: per-CTA digit counts -> scan over CTAs -> ranked scatter -------------------------------
+// (A single-kernel "onesweep" with decoupled look-back was tried first: with 512 digits every CTA needs 512
+//  independent look-back walks, and with ~740 CTAs in flight the walks are hundreds of dependent L2 round trips
+//  deep -- it ran at 1.2 TB/s.  Counting first costs one extra read of the keys and removes every spin.)
 
-// exclusive scan of each pass's histogram, in place (one CTA per pass)
-template <int RADIX_BITS>
-__global__ void __launch_bounds__(THREADS) scan_hist_kernel(uint32_t *hist)
-{
-    constexpr int BINS = 1 << RADIX_BITS;
-    __shared__ uint32_t s[BINS];
-    uint32_t *h = hist + (size_t)blockIdx.x * BINS;
-    for (int i = threadIdx.x; i < BINS; i += THREADS) s[i] = h[i];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t run = 0;
-        for (int i = 0; i < BINS; i++) {
-            const uint32_t c = s[i];
-            s[i] = run;
-            run += c;
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < BINS; i += THREADS) h[i] = s[i];
-}
-
-// ---- one onesweep pass ------------------------------------------------------------------------------------------
+// counts[d][cta] = number of items of CTA `cta` whose digit is d          (digit-major: the scan is contiguous)
 template <typename KeyT, int RADIX_BITS, int IPT>
-__global__ void __launch_bounds__(THREADS) onesweep_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
-                                                            const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out,
-                                                            int64_t n, int shift, int bits,
-                                                            const uint32_t *__restrict__ digit_base /* [BINS] exclusive */,
-                                                            volatile uint32_t *status /* [nblocks][BINS], zeroed */,
-                                                            uint32_t *ticket /* zeroed */)
+__global__ void __launch_bounds__(THREADS) count_kernel(const KeyT *__restrict__ keys, int64_t n, int shift, int bits,
+                                                         uint32_t *__restrict__ counts, uint32_t nblocks)
+{
+    constexpr int BINS = 1 << RADIX_BITS;
+    constexpr int TILE = THREADS * IPT;
+    __shared__ uint32_t sh[BINS];
+    for (int i = threadIdx.x; i < BINS; i += THREADS) sh[i] = 0;
+    __syncthreads();
+    const int64_t tile_start = (int64_t)blockIdx.x * TILE;
+    const int n_tile = (int)min((int64_t)TILE, n - tile_start);
+    KeyT key[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {
+        const int idx = i * THREADS + threadIdx.x;
+        key[i] = (idx < n_tile) ? keys[tile_start + idx] : (KeyT)0;
+    }
+#pragma unroll
+    for (int i = 0; i < IPT; i++)
+        if (i * THREADS + (int)threadIdx.x < n_tile) atomicAdd(&sh[digit_of(key[i], shift, bits)], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < BINS; i += THREADS) counts[(size_t)i * nblocks + blockIdx.x] = sh[i];
+}
+
+// one CTA per digit: exclusive scan of its row of per-CTA counts in place; totals[d] = row sum
+__global__ void __launch_bounds__(THREADS) scan_counts_kernel(uint32_t *__restrict__ counts, uint32_t nblocks, uint32_t *__restrict__ totals)
+{
+    __shared__ uint32_t s_wsum[WARPS];
+    uint32_t *row = counts + (size_t)blockIdx.x * nblocks;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t per = (nblocks + THREADS - 1) / THREADS;
+    const uint32_t b0 = min(nblocks, (uint32_t)tid * per), b1 = min(nblocks, b0 + per);
+    uint32_t tsum = 0;
+    for (uint32_t b = b0; b < b1; b++) tsum += row[b];
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+    for (int w = 0; w < WARPS; w++) {
+        if (w < warp) wbase += s_wsum[w];
+        total += s_wsum[w];
+    }
+    uint32_t run = wbase + incl - tsum;
+    for (uint32_t b = b0; b < b1; b++) {
+        const uint32_t c = row[b];
+        row[b] = run;
+        run += c;
+    }
+    if (tid == 0) totals[blockIdx.x] = total;
+}
+
+// ranked scatter of one CTA tile: stable inside the tile, destinations from the scanned counts
+template <typename KeyT, int RADIX_BITS, int IPT>
+__global__ void __launch_bounds__(THREADS) scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
+                                                           const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out,
+                                                           int64_t n, int shift, int bits, const uint32_t *__restrict__ counts /* scanned */,
+                                                           uint32_t nblocks, const uint32_t *__restrict__ totals)
 {
     constexpr int BINS = 1 << RADIX_BITS;
     constexpr int TILE = THREADS * IPT;
@@ -88,26 +100,42 @@ __global__ void __launch_bounds__(THREADS) onesweep_kernel(const KeyT *__restric
     __shared__ uint32_t s_glob[BINS];       // global destination of the CTA's first item of each digit
     __shared__ KeyT s_keys[TILE];
     __shared__ uint32_t s_vals[TILE];
-    __shared__ uint32_t s_bid, s_wsum[WARPS];
+    __shared__ uint32_t s_wsum[WARPS];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) s_bid = atomicAdd(ticket, 1u);
+    const uint32_t bid = blockIdx.x;
     for (int i = tid; i < WARPS * BINS; i += THREADS) (&s_cnt[0][0])[i] = 0;
-    __syncthreads();
-    const uint32_t bid = s_bid;
     const int64_t tile_start = (int64_t)bid * TILE;
     const int n_tile = (int)min((int64_t)TILE, n - tile_start);
 
-    // ---- load (warp-striped: coalesced) and rank
+    // ---- load (warp-striped: coalesced); all loads are issued before the first use
     KeyT key[IPT];
     uint32_t val[IPT], rnk[IPT];
     const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
     for (int i = 0; i < IPT; i++) {
         const int idx = warp * (IPT * 32) + i * 32 + lane;
+        key[i] = (idx < n_tile) ? keys_in[tile_start + idx] : (KeyT)0;
+    }
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {
+        const int idx = warp * (IPT * 32) + i * 32 + lane;
+        val[i] = (idx < n_tile) ? vals_in[tile_start + idx] : 0u;
+    }
+    // digit totals -> (later) global digit bases
+    uint32_t tot[DPT], cnt_glob[DPT];
+#pragma unroll
+    for (int q = 0; q < DPT; q++) {
+        const int d = tid + q * THREADS;
+        tot[q] = (d < BINS) ? totals[d] : 0u;
+        cnt_glob[q] = (d < BINS) ? counts[(size_t)d * nblocks + bid] : 0u;
+    }
+    __syncthreads();
+    // ---- rank: stable position of every item among the items of its digit inside this warp
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {
+        const int idx = warp * (IPT * 32) + i * 32 + lane;
         const bool valid = idx < n_tile;
-        key[i] = valid ? keys_in[tile_start + idx] : (KeyT)0;
-        val[i] = valid ? vals_in[tile_start + idx] : 0u;
         const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
         rnk[i] = 0xffffffffu;
         if (valid) {
@@ -121,7 +149,6 @@ __global__ void __launch_bounds__(THREADS) onesweep_kernel(const KeyT *__restric
         }
     }
     __syncthreads();
-
     // ---- per digit: exclusive prefix over warps, CTA count
     uint32_t cta_count[DPT];
 #pragma unroll
@@ -139,57 +166,34 @@ __global__ void __launch_bounds__(THREADS) onesweep_kernel(const KeyT *__restric
             cta_count[q] = run;
         }
     }
-    // ---- publish the CTA aggregate, then look back for the exclusive prefix over earlier CTAs
-#pragma unroll
-    for (int q = 0; q < DPT; q++) {
-        const int d = tid + q * THREADS;
-        if (d < BINS) {
-            status[(size_t)bid * BINS + d] = (bid == 0 ? FLAG_PREFIX : FLAG_AGG) | cta_count[q];
-        }
-    }
-    __threadfence();
-    // ---- local exclusive scan of cta_count over digits (digits are spread tid + q*THREADS)
+    // ---- two exclusive scans over digits (digits are spread tid + q*THREADS): local offsets and global bases
     {
-        // scan within each q-slab with warp shuffles, slabs are consecutive digit ranges
-        uint32_t slab_base = 0;
+        uint32_t slab_base_l = 0, slab_base_g = 0;
 #pragma unroll
         for (int q = 0; q < DPT; q++) {
-            uint32_t x = cta_count[q];
-            uint32_t incl = x;
+            uint32_t il = cta_count[q], ig = tot[q];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += y;
+                const uint32_t yl = __shfl_up_sync(0xffffffffu, il, o), yg = __shfl_up_sync(0xffffffffu, ig, o);
+                if (lane >= o) { il += yl; ig += yg; }
             }
-            if (lane == 31) s_wsum[warp] = incl;
             __syncthreads();
-            uint32_t wbase = 0;
-            for (int w = 0; w < warp; w++) wbase += s_wsum[w];
-            uint32_t slab_total = 0;
-            for (int w = 0; w < WARPS; w++) slab_total += s_wsum[w];
+            if (lane == 31) s_wsum[warp] = il;
+            __syncthreads();
+            uint32_t wl = 0, tl = 0;
+            for (int w = 0; w < WARPS; w++) { if (w < warp) wl += s_wsum[w]; tl += s_wsum[w]; }
+            __syncthreads();
+            if (lane == 31) s_wsum[warp] = ig;
+            __syncthreads();
+            uint32_t wg = 0, tg = 0;
+            for (int w = 0; w < WARPS; w++) { if (w < warp) wg += s_wsum[w]; tg += s_wsum[w]; }
             const int d = tid + q * THREADS;
-            if (d < BINS) s_loc[d] = slab_base + wbase + incl - x;
-            slab_base += slab_total;
-            __syncthreads();
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < DPT; q++) {
-        const int d = tid + q * THREADS;
-        if (d < BINS) {
-            uint32_t excl = 0;
-            if (bid > 0) {
-                int64_t p = (int64_t)bid - 1;
-                while (true) {
-                    uint32_t s;
-                    do { s = status[(size_t)p * BINS + d]; } while ((s & FLAG_MASK) == 0);
-                    excl += s & VALUE_MASK;
-                    if ((s & FLAG_MASK) == FLAG_PREFIX) break;
-                    p--;
-                }
-                status[(size_t)bid * BINS + d] = FLAG_PREFIX | (excl + cta_count[q]);
+            if (d < BINS) {
+                s_loc[d] = slab_base_l + wl + il - cta_count[q];
+                s_glob[d] = slab_base_g + wg + ig - tot[q] + cnt_glob[q];
             }
-            s_glob[d] = digit_base[d] + excl;
+            slab_base_l += tl;
+            slab_base_g += tg;
         }
     }
     __syncthreads();
