@@ -89,8 +89,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------- CPU reference
-def oracle_views_per_s(args, n_views, threads=0):
-    """fwd+bwd of n_views views of the SAME workload by the CPU oracle (all host threads)."""
+def oracle_views_per_s(args, n_views, threads=None):
+    """fwd+bwd of n_views views of the SAME workload by the CPU oracle (all host threads; set explicitly because
+    torchrun exports OMP_NUM_THREADS=1)."""
+    threads = threads or os.cpu_count()
     import numpy as np
     import torch
     from humangaussian_b200.cameras import sample_orbit_cameras
@@ -207,6 +209,7 @@ def run_b200(args):
     torch.cuda.set_device(dev)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("B200GS_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     R.load_library()
     P, V, HW, deg = args.gaussians, args.views, args.res, args.sh_degree
