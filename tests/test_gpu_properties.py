@@ -1,0 +1,168 @@
+"""GPU: size-independent properties at BASELINE.json's full size (300k Gaussians, SH degree 3, 1024x1024), where the CPU
+oracle would take minutes, plus the edge cases of the domain (partial tiles, sub-tile images, screen-filling and
+degenerate Gaussians, active degree < stored degree, scale_modifier, > 64 views, non-contiguous / half inputs)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from util import grad_images, grads_agree, small_scene
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def full():
+    from humangaussian_b200.cameras import sample_orbit_cameras
+    from humangaussian_b200.renderer import stack_cameras
+    from humangaussian_b200.scene import synthetic_body
+    p = synthetic_body(300_000, sh_degree=3, seed=0).to(DEV)
+    cams = sample_orbit_cameras(4, 1024, 1024, seed=1000, device=DEV)
+    with torch.no_grad():
+        t = dict(means3D=p.get_xyz, opacities=p.get_opacity, shs=p.get_features.contiguous(), scales=p.get_scaling, rotations=p.get_rotation)
+    vm, pm, cp, tanx, tany = stack_cameras(cams, DEV)
+    return t, dict(viewmatrix=vm, projmatrix=pm, campos=cp, tanfovx=tanx, tanfovy=tany, image_height=1024, image_width=1024, sh_degree=3)
+
+
+def test_full_size_binning_invariants(full):
+    from humangaussian_b200.rasterizer import forward_with_state
+    t, c = full
+    color, radii, depth, alpha, st, _ = forward_with_state(**t, **c, bg=torch.zeros(3, device=DEV))
+    V, P, D, ntiles = 4, 300_000, st["num_rendered"], 64 * 64
+    assert D > 3_000_000 and int((radii > 0).sum()) > 0.7 * V * P
+    assert int(st["tiles_touched"].to(torch.int64).sum()) == D
+    keys = st["sorted_keys"]  # int64 holding the reference's u64 (tile|depth) keys; top bit never set here
+    assert bool((keys[1:] >= keys[:-1]).all()), "sorted keys are not monotone"
+    pl = st["point_list"].to(torch.int64)
+    same = keys[1:] == keys[:-1]
+    assert bool((pl[1:][same] > pl[:-1][same]).all()), "equal (tile, depth) keys must keep ascending Gaussian index"
+    r = st["ranges"].to(torch.int64)
+    ne = r[:, 1] > r[:, 0]
+    assert int((r[ne, 1] - r[ne, 0]).sum()) == D and int(r[ne, 0].min()) == 0 and int(r[ne, 1].max()) == D
+    tile_of = (keys >> 32)
+    starts = r[ne, 0]
+    assert bool((tile_of[starts] == torch.nonzero(ne).squeeze(1)).all()), "range start does not sit on its tile's first key"
+    # per-pixel state
+    n_c = st["n_contrib"].to(torch.int64).reshape(V, 64, 16, 64, 16).permute(0, 1, 3, 2, 4).reshape(V * ntiles, 256)
+    assert bool((n_c.max(1).values <= (r[:, 1] - r[:, 0])).all()), "n_contrib exceeds the tile list length"
+    fT = st["final_T"]
+    assert float(fT.min()) > 0 and float(fT.max()) <= 1.0
+    assert float((alpha[:, 0] - (1 - fT)).abs().max()) < 2e-4, "alpha must equal 1 - T"
+    assert bool(torch.isfinite(color).all()) and float(depth.min()) >= 0
+
+
+def test_full_size_background_linearity_and_determinism(full):
+    from humangaussian_b200.rasterizer import forward_with_state
+    t, c = full
+    c0, _, d0, a0, st0, _ = forward_with_state(**t, **c, bg=torch.zeros(3, device=DEV))
+    c1, _, d1, a1, st1, _ = forward_with_state(**t, **c, bg=torch.ones(3, device=DEV))
+    assert torch.equal(d0, d1) and torch.equal(a0, a1) and torch.equal(st0["point_list"], st1["point_list"])
+    assert float((c1 - c0 - st0["final_T"][:, None]).abs().max()) < 1e-6, "colour must be C + T*bg"
+    c2, _, _, _, _, _ = forward_with_state(**t, **c, bg=torch.zeros(3, device=DEV))
+    assert torch.equal(c0, c2), "forward is not deterministic"
+
+
+def test_full_size_backward_linearity(full):
+    from humangaussian_b200.rasterizer import rasterize_views
+    t, c = full
+    leaves = {k: v.clone().requires_grad_(True) for k, v in t.items()}
+    g = torch.Generator(device=DEV).manual_seed(0)
+    gw = [torch.randn(4, ch, 1024, 1024, device=DEV, generator=g) for ch in (3, 1, 1)]
+
+    def grads(scale):
+        for v in leaves.values():
+            v.grad = None
+        out = rasterize_views(means3D=leaves["means3D"], opacities=leaves["opacities"], viewmatrices=c["viewmatrix"],
+                              projmatrices=c["projmatrix"], camposs=c["campos"], tanfovx=c["tanfovx"], tanfovy=c["tanfovy"],
+                              image_height=1024, image_width=1024, bg=torch.zeros(3, device=DEV), sh_degree=3, shs=leaves["shs"],
+                              scales=leaves["scales"], rotations=leaves["rotations"])
+        torch.autograd.backward([out[0], out[2], out[3]], [w * scale for w in gw])
+        return {k: v.grad.clone() for k, v in leaves.items()}
+
+    g1, g2, g0 = grads(1.0), grads(2.0), grads(0.0)
+    for k in g1:
+        assert float(g0[k].abs().max()) == 0.0, f"zero upstream gradient must give zero dL/d{k}"
+        assert bool(torch.isfinite(g1[k]).all())
+        ok, msg = grads_agree((g2[k] * 0.5).cpu().numpy(), g1[k].cpu().numpy(), atol=1e-5, rtol=2e-4)
+        assert ok, f"dL/d{k} is not linear in the upstream gradient: {msg}"
+
+
+def _parity(inp, seed=0, keys=("means3D", "opacities", "shs", "scales", "rotations")):
+    from test_gpu_parity import _check_backward, _check_forward_state, _oracle
+    o_out, o_st, gimg, o_grads = _oracle(inp, seed)
+    _check_forward_state(inp, o_out, o_st)
+    _check_backward(inp, o_out, gimg, o_grads, keys=keys)
+    return o_st
+
+
+@pytest.mark.parametrize("H,W", [(8, 8), (17, 33), (16, 16), (1, 40), (100, 7)])
+def test_odd_image_sizes(H, W):
+    inp, _, _ = small_scene(P=400, deg=1, seed=H + W, H=H, W=W)
+    _parity(inp, 1)
+
+
+def test_screen_filling_and_tiny_gaussians():
+    inp, _, _ = small_scene(P=300, deg=0, seed=3, H=64, W=96)
+    inp["scales"][:5] *= 200.0        # radii far larger than the image: rect clamps to the whole grid
+    inp["scales"][5:40] *= 1e-3       # sub-pixel: the +0.3 dilation keeps them 1-pixel blobs
+    inp["opacities"][40:60] = 0.0     # can never reach 1/255
+    inp["opacities"][60:80] = 1.0     # alpha clamps at 0.99
+    inp["opacities"][80:90] = 1.0 / 255.0 + 1e-6
+    st = _parity(inp, 2)
+    assert st["tiles_touched"].max() == (64 // 16) * (96 // 16)
+
+
+def test_scale_modifier_and_active_degree_below_stored():
+    inp, _, _ = small_scene(P=500, deg=3, seed=8, H=48, W=64)
+    inp["scale_modifier"] = 0.6
+    inp["sh_degree"] = 1              # shs still holds 16 coefficients per channel (M = 16): only the first 4 are used
+    st = _parity(inp, 4)
+    from oracle.gs_oracle import Oracle
+    inp2 = dict(inp); inp2["shs"] = inp["shs"].copy(); inp2["shs"][:, 4:] = 123.0  # unused bands must not matter
+    assert np.array_equal(Oracle().forward(**inp2)[0], Oracle().forward(**inp)[0])
+
+
+def test_more_than_64_views_chunks_transparently():
+    from humangaussian_b200.cameras import sample_orbit_cameras
+    from humangaussian_b200.rasterizer import rasterize_views
+    from humangaussian_b200.renderer import stack_cameras
+    inp, _, _ = small_scene(P=800, deg=0, seed=2, H=32, W=32)
+    cams = sample_orbit_cameras(70, 32, 32, seed=5, device=DEV)
+    vm, pm, cp, tanx, tany = stack_cameras(cams, DEV)
+    g = lambda k: torch.tensor(inp[k], device=DEV)
+    args = dict(means3D=g("means3D"), opacities=g("opacities"), image_height=32, image_width=32, bg=g("bg"), sh_degree=0, shs=g("shs"),
+                scales=g("scales"), rotations=g("rotations"))
+    c, r, d, a = rasterize_views(viewmatrices=vm, projmatrices=pm, camposs=cp, tanfovx=tanx, tanfovy=tany, **args)
+    assert c.shape == (70, 3, 32, 32) and r.shape == (70, 800)
+    c2 = rasterize_views(viewmatrices=vm[64:], projmatrices=pm[64:], camposs=cp[64:], tanfovx=tanx[64:], tanfovy=tany[64:], **args)[0]
+    assert torch.equal(c[64:], c2)
+
+
+def test_half_and_noncontiguous_inputs_are_cast_like_the_reference_wrapper():
+    """render() calls .float() on everything (gaussian_renderer/__init__.py:87-93); strided / fp16 tensors must work."""
+    from humangaussian_b200.rasterizer import GaussianRasterizer
+    from test_gpu_parity import _settings
+    inp, _, _ = small_scene(P=300, deg=1, seed=6, H=32, W=48)
+    g = lambda k: torch.tensor(inp[k], device=DEV)
+    r = GaussianRasterizer(_settings(inp))
+    base = r(means3D=g("means3D"), means2D=torch.zeros(300, 3, device=DEV), shs=g("shs"), opacities=g("opacities"), scales=g("scales"), rotations=g("rotations"))
+    big = torch.zeros(300, 6, device=DEV); big[:, ::2] = g("means3D")
+    strided = r(means3D=big[:, ::2], means2D=torch.zeros(300, 3, device=DEV), shs=g("shs"), opacities=g("opacities"), scales=g("scales"), rotations=g("rotations"))
+    assert torch.equal(base[0], strided[0])
+    half = r(means3D=g("means3D"), means2D=torch.zeros(300, 3, device=DEV), shs=g("shs").half(), opacities=g("opacities"), scales=g("scales"), rotations=g("rotations"))
+    ref = r(means3D=g("means3D"), means2D=torch.zeros(300, 3, device=DEV), shs=g("shs").half().float(), opacities=g("opacities"), scales=g("scales"), rotations=g("rotations"))
+    assert torch.equal(half[0], ref[0])
+
+
+def test_only_some_inputs_require_grad():
+    from humangaussian_b200.rasterizer import GaussianRasterizer
+    from test_gpu_parity import _settings
+    inp, _, _ = small_scene(P=300, deg=0, seed=6, H=32, W=48)
+    g = lambda k: torch.tensor(inp[k], device=DEV)
+    xyz = g("means3D").requires_grad_(True)
+    c, _, d, a = GaussianRasterizer(_settings(inp))(means3D=xyz, means2D=torch.zeros(300, 3, device=DEV), shs=g("shs"), opacities=g("opacities"),
+                                                  scales=g("scales"), rotations=g("rotations"))
+    c.sum().backward()
+    assert xyz.grad is not None and float(xyz.grad.abs().max()) > 0
