@@ -112,6 +112,7 @@ int b200gs_forward(const b200gs_params *prm, const float *means3D, const float *
         PreArgs a;
         a.P = P; a.deg = shs ? prm->sh_degree : 0; a.M = prm->sh_coeffs; a.H = H; a.W = W; a.grid_x = gx; a.grid_y = gy;
         a.mod = prm->scale_modifier;
+        a.means_view_stride = prm->means3D_per_view ? (size_t)3 * P : 0;
         a.means = means3D; a.shs = shs; a.colors_pre = colors_precomp; a.opac = opacities; a.scales = scales;
         a.rots = rotations; a.cov_pre = cov3D_precomp; a.view = viewmatrix; a.proj = projmatrix; a.campos = campos;
         for (int v = 0; v < V; v++) { a.tanfovx[v] = prm->tanfovx[v]; a.tanfovy[v] = prm->tanfovy[v]; }
@@ -194,6 +195,7 @@ int b200gs_backward(const b200gs_params *prm, const float *means3D, const float 
 
     PreBwdArgs a;
     a.P = P; a.V = V; a.deg = shs ? prm->sh_degree : 0; a.M = prm->sh_coeffs; a.H = H; a.W = W; a.mod = prm->scale_modifier;
+    a.means_view_stride = prm->means3D_per_view ? (size_t)3 * P : 0;
     a.means = means3D; a.shs = shs; a.colors_pre = colors_precomp; a.scales = scales; a.rots = rotations; a.cov_pre = cov3D_precomp;
     a.view = viewmatrix; a.proj = projmatrix; a.campos = campos;
     for (int v = 0; v < V; v++) { a.tanfovx[v] = prm->tanfovx[v]; a.tanfovy[v] = prm->tanfovy[v]; }
@@ -267,6 +269,29 @@ int b200gs_profile_read(double *ms_per_stage, int64_t *calls_per_stage, int32_t 
         g_event_pool.push_back(sp.e0); g_event_pool.push_back(sp.e1);
     }
     g_spans.clear();
+    return B200GS_OK;
+}
+
+int b200gs_reattach(int32_t P, int32_t n_frames, int32_t n_verts, int32_t n_faces, const float *vertices, const int32_t *faces,
+                    const int32_t *mapping_face, const float *mapping_uvw, const float *mapping_dist, float *xyz_out, void *stream)
+{
+    if (P < 0 || n_frames < 1 || n_verts < 1 || n_faces < 1 || !vertices || !faces || !mapping_face || !mapping_uvw || !mapping_dist || !xyz_out)
+        return B200GS_E_ARGS;
+    if (n_frames > 65535) return B200GS_E_RANGE;
+    if (P == 0) return B200GS_OK;
+    launch_reattach(P, n_frames, n_verts, vertices, faces, mapping_face, mapping_uvw, mapping_dist, xyz_out, (cudaStream_t)stream);
+    g_launches += 1;
+    CK(cudaGetLastError(), "reattach launch");
+    return B200GS_OK;
+}
+
+int b200gs_pack_frames_u8(const float *color, uint8_t *out, int32_t image_height, int32_t image_width, int32_t n_frames, void *stream)
+{
+    if (!color || !out || image_height < 1 || image_width < 1 || n_frames < 1) return B200GS_E_ARGS;
+    if (n_frames > 65535) return B200GS_E_RANGE;
+    launch_pack_u8(color, out, image_height, image_width, n_frames, (cudaStream_t)stream);
+    g_launches += 1;
+    CK(cudaGetLastError(), "pack launch");
     return B200GS_OK;
 }
 

@@ -4,6 +4,7 @@
 
 struct PreArgs {
     int P, deg, M, H, W, grid_x, grid_y;
+    size_t means_view_stride; // 0: means shared by all views; 3*P: per-view positions
     float mod;
     const float *means, *shs, *colors_pre, *opac, *scales, *rots, *cov_pre;
     const float *view, *proj, *campos; // [V,16] [V,16] [V,3]
@@ -20,6 +21,7 @@ struct PreArgs {
 
 struct PreBwdArgs {
     int P, V, deg, M, H, W;
+    size_t means_view_stride; // as PreArgs; when non-zero dL_dmeans3D is [V,P,3] (per view, not summed)
     float mod;
     const float *means, *shs, *colors_pre, *scales, *rots, *cov_pre;
     const float *view, *proj, *campos;
@@ -79,3 +81,8 @@ void launch_blend_fwd(const BlendArgs &a, cudaStream_t st);
 void launch_blend_bwd(const BlendBwdArgs &a, cudaStream_t st);
 int blend_sgrad_is_moments(); // which ScreenGrad format the linked blend_bwd writes
 void launch_test_exp(const float *x, float *y, int64_t n, cudaStream_t st);
+
+// animation frame path (anim.cu)
+void launch_reattach(int P, int n_frames, int n_verts, const float *vertices, const int32_t *faces, const int32_t *map_face,
+                     const float *map_uvw, const float *map_dist, float *xyz, cudaStream_t st);
+void launch_pack_u8(const float *color, uint8_t *out, int H, int W, int n_frames, cudaStream_t st);

@@ -88,8 +88,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreArgs a, int nvie
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.P) return;
 
-    const float px = __ldg(a.means + 3 * (size_t)i), py = __ldg(a.means + 3 * (size_t)i + 1),
-                pz = __ldg(a.means + 3 * (size_t)i + 2);
+    float px = __ldg(a.means + 3 * (size_t)i), py = __ldg(a.means + 3 * (size_t)i + 1), pz = __ldg(a.means + 3 * (size_t)i + 2);
     const float op = __ldg(a.opac + i);
     float c6[6];
     if (a.cov_pre) {
@@ -126,6 +125,10 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreArgs a, int nvie
     for (int v = 0; v < nviews; v++) {
         const size_t vp = (size_t)v * a.P + i;
         const float *V = a.view + 16 * v, *PV = a.proj + 16 * v;
+        if (a.means_view_stride && v > 0) { // animation frame batch: this view has its own positions
+            const float *m = a.means + (size_t)v * a.means_view_stride + 3 * (size_t)i;
+            px = __ldg(m); py = __ldg(m + 1); pz = __ldg(m + 2);
+        }
         int radius = 0;
         uint32_t tiles = 0;
         uint2 rect_pack = make_uint2(0, 0);
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(PreBwdArgs a)
     constexpr int nb = DEG < 0 ? 1 : (DEG + 1) * (DEG + 1);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.P) return;
-    const float px = a.means[3 * (size_t)i], py = a.means[3 * (size_t)i + 1], pz = a.means[3 * (size_t)i + 2];
+    float px = a.means[3 * (size_t)i], py = a.means[3 * (size_t)i + 1], pz = a.means[3 * (size_t)i + 2];
 
     float c6[6];
     float R[3][3], s[3] = {0, 0, 0}, q[4] = {0, 0, 0, 0};
@@ -311,6 +314,15 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(PreBwdArgs a)
     for (int v = 0; v < a.V; v++) {
         const size_t vp = (size_t)v * a.P + i;
         float *m2d = a.dL_dmeans2D + 3 * vp;
+        if (a.means_view_stride) { // per-view positions: per-view (not summed) position gradients
+            if (v > 0) {
+                float *o = a.dL_dmeans3D + 3 * ((size_t)(v - 1) * a.P + i);
+                o[0] = dmean[0]; o[1] = dmean[1]; o[2] = dmean[2];
+                dmean[0] = dmean[1] = dmean[2] = 0.f;
+                const float *m = a.means + (size_t)v * a.means_view_stride + 3 * (size_t)i;
+                px = m[0]; py = m[1]; pz = m[2];
+            }
+        }
         if (!(a.radii[vp] > 0)) {
             m2d[0] = 0.f; m2d[1] = 0.f; m2d[2] = 0.f;
             continue;
@@ -449,9 +461,10 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(PreBwdArgs a)
         }
     }
 
-    a.dL_dmeans3D[3 * (size_t)i] = dmean[0];
-    a.dL_dmeans3D[3 * (size_t)i + 1] = dmean[1];
-    a.dL_dmeans3D[3 * (size_t)i + 2] = dmean[2];
+    {
+        float *o = a.dL_dmeans3D + 3 * ((a.means_view_stride ? (size_t)(a.V - 1) * a.P : 0) + (size_t)i);
+        o[0] = dmean[0]; o[1] = dmean[1]; o[2] = dmean[2];
+    }
     a.dL_dopacity[i] = dop;
     if (DEG >= 0) {
         float *o = a.dL_dsh + (size_t)i * a.M * 3;

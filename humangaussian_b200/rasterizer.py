@@ -27,7 +27,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # B200GS_LIB selects another build of the SAME C-ABI (only used to time baseline/libb200gs_classic.so, the
 # classic-structure comparator, through the identical host path).  It is not a fallback: the default is the product.
 LIB_PATH = os.environ.get("B200GS_LIB") or os.path.join(_HERE, "libb200gs.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_VIEWS = 64
 
 OK, E_ARGS, E_BIN_TOO_SMALL, E_BUFFER, E_CUDA, E_RANGE = 0, -1, -2, -3, -4, -5
@@ -37,7 +37,7 @@ class _Params(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("P", C.c_int32), ("n_views", C.c_int32), ("sh_degree", C.c_int32),
                 ("sh_coeffs", C.c_int32), ("image_height", C.c_int32), ("image_width", C.c_int32),
                 ("prefiltered", C.c_int32), ("debug", C.c_int32), ("scale_modifier", C.c_float),
-                ("tanfovx", C.POINTER(C.c_float)), ("tanfovy", C.POINTER(C.c_float))]
+                ("tanfovx", C.POINTER(C.c_float)), ("tanfovy", C.POINTER(C.c_float)), ("means3D_per_view", C.c_int32)]
 
 
 class _StateView(C.Structure):
@@ -49,7 +49,7 @@ _lib = None
 EXPORTS = ["b200gs_forward", "b200gs_backward", "b200gs_mark_visible", "b200gs_describe_state", "b200gs_test_exp",
            "b200gs_geom_bytes", "b200gs_image_bytes", "b200gs_binning_bytes", "b200gs_backward_scratch_bytes",
            "b200gs_last_cuda_error", "b200gs_abi_version", "b200gs_launch_count", "b200gs_profile_enable", "b200gs_profile_read",
-           "b200gs_test_sort_pairs", "b200gs_test_sort_scratch_bytes"]
+           "b200gs_test_sort_pairs", "b200gs_test_sort_scratch_bytes", "b200gs_reattach", "b200gs_pack_frames_u8"]
 STAGES = ["preprocess_fwd", "scan", "binning", "blend_fwd", "blend_bwd", "preprocess_bwd"]
 
 
@@ -83,6 +83,10 @@ def load_library():
     L.b200gs_test_sort_pairs.restype = C.c_int
     L.b200gs_test_sort_pairs.argtypes = [vp, vp, vp, vp, i64, i32, vp, sz, C.POINTER(i32), vp]
     L.b200gs_test_sort_scratch_bytes.restype = sz; L.b200gs_test_sort_scratch_bytes.argtypes = [i64]
+    L.b200gs_reattach.restype = C.c_int
+    L.b200gs_reattach.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.b200gs_pack_frames_u8.restype = C.c_int
+    L.b200gs_pack_frames_u8.argtypes = [vp, vp, i32, i32, i32, vp]
     L.b200gs_last_cuda_error.restype = C.c_char_p
     L.b200gs_launch_count.restype = i64
     L.b200gs_profile_enable.restype = None; L.b200gs_profile_enable.argtypes = [C.c_int]
@@ -162,11 +166,11 @@ class _Ctx:
     __slots__ = ("prm", "tanx", "tany", "geom", "binning", "image", "capacity", "num_rendered", "radii", "V", "P", "H", "W", "M")
 
 
-def _make_params(P, V, deg, M, H, W, mod, tanx, tany, prefiltered=False, debug=False):
+def _make_params(P, V, deg, M, H, W, mod, tanx, tany, prefiltered=False, debug=False, per_view_means=False):
     tx = (C.c_float * V)(*[float(t) for t in tanx])
     ty = (C.c_float * V)(*[float(t) for t in tany])
     prm = _Params(ABI_VERSION, P, V, int(deg), int(M), int(H), int(W), int(bool(prefiltered)), int(bool(debug)), float(mod),
-                  C.cast(tx, C.POINTER(C.c_float)), C.cast(ty, C.POINTER(C.c_float)))
+                  C.cast(tx, C.POINTER(C.c_float)), C.cast(ty, C.POINTER(C.c_float)), int(bool(per_view_means)))
     return prm, tx, ty
 
 
@@ -177,14 +181,18 @@ def _forward_impl(means3D, shs, colors_precomp, opacities, scales, rotations, co
     dev = means3D.device
     if dev.type != "cuda":
         raise RuntimeError("b200gs: tensors must live on a CUDA device (there is no CPU path)")
-    P, V = means3D.shape[0], viewmatrix.shape[0]
+    V = viewmatrix.shape[0]
+    per_view_means = means3D.dim() == 3  # [V,P,3]: animation frame batch
+    if per_view_means and means3D.shape[0] != V:
+        raise ValueError(f"per-view means3D has {means3D.shape[0]} views, cameras have {V}")
+    P = means3D.shape[-2]
     if (shs is None) == (colors_precomp is None):
         raise Exception("Please provide excatly one of either SHs or precomputed colors!")
     if ((scales is None or rotations is None) and cov3D_precomp is None) or \
             ((scales is not None or rotations is not None) and cov3D_precomp is not None):
         raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
     M = 0 if shs is None else shs.shape[1]
-    prm, tx, ty = _make_params(P, V, sh_degree, M, H, W, scale_modifier, tanfovx, tanfovy, prefiltered, debug)
+    prm, tx, ty = _make_params(P, V, sh_degree, M, H, W, scale_modifier, tanfovx, tanfovy, prefiltered, debug, per_view_means)
     u8 = dict(dtype=torch.uint8, device=dev)
     geom = torch.empty(L.b200gs_geom_bytes(P, V), **u8)
     image = torch.empty(L.b200gs_image_bytes(H, W, V), **u8)
@@ -222,7 +230,7 @@ def _backward_impl(st: _Ctx, means3D, shs, colors_precomp, opacities, scales, ro
     dev = means3D.device
     P, V, M = st.P, st.V, st.M
     f = dict(dtype=torch.float32, device=dev)
-    d_means3D = torch.empty(P, 3, **f)
+    d_means3D = torch.empty(means3D.shape, **f)  # [P,3], or [V,P,3] for per-view positions
     d_means2D = torch.empty(V, P, 3, **f)
     d_op = torch.empty(P, 1, **f)
     d_sh = torch.empty(P, M, 3, **f) if shs is not None else None
@@ -333,12 +341,14 @@ def rasterize_views(*, means3D, opacities, viewmatrices, projmatrices, camposs, 
                     means2D=None, scale_modifier=1.0):
     """Render V cameras of one Gaussian set in ONE call (one preprocess/sort/blend launch set, one host sync).
 
-    viewmatrices/projmatrices [V,4,4], camposs [V,3], tanfovx/tanfovy sequences of V floats.  means2D, if given,
+    viewmatrices/projmatrices [V,4,4], camposs [V,3], tanfovx/tanfovy sequences of V floats.  means3D is [P,3]
+    (shared: the SDS view batch) or [V,P,3] (per-view positions: the animation frame batch).  means2D, if given,
     is a [V,P,3] gradient sink.  Returns color [V,3,H,W], radii [V,P], depth [V,1,H,W], alpha [V,1,H,W].
     Parameter gradients are summed over views, exactly what V separate rasterizer calls would accumulate."""
     V = viewmatrices.shape[0]
     if V > MAX_VIEWS:
-        outs = [rasterize_views(means3D=means3D, opacities=opacities, viewmatrices=viewmatrices[i:i + MAX_VIEWS],
+        outs = [rasterize_views(means3D=means3D if means3D.dim() == 2 else means3D[i:i + MAX_VIEWS], opacities=opacities,
+                                viewmatrices=viewmatrices[i:i + MAX_VIEWS],
                                 projmatrices=projmatrices[i:i + MAX_VIEWS], camposs=camposs[i:i + MAX_VIEWS],
                                 tanfovx=tanfovx[i:i + MAX_VIEWS], tanfovy=tanfovy[i:i + MAX_VIEWS], image_height=image_height,
                                 image_width=image_width, bg=bg, sh_degree=sh_degree, shs=shs, colors_precomp=colors_precomp,
@@ -347,7 +357,7 @@ def rasterize_views(*, means3D, opacities, viewmatrices, projmatrices, camposs, 
                 for i in range(0, V, MAX_VIEWS)]
         return tuple(torch.cat([o[k] for o in outs], 0) for k in range(4))
     if means2D is None:
-        means2D = torch.zeros(V, means3D.shape[0], 3, dtype=torch.float32, device=means3D.device)
+        means2D = torch.zeros(V, means3D.shape[-2], 3, dtype=torch.float32, device=means3D.device)
     cams = (bg, viewmatrices, projmatrices, camposs, list(tanfovx), list(tanfovy), int(image_height), int(image_width),
             int(sh_degree), float(scale_modifier), False, False)
     return _RasterizeViews.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, cams, False)

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200GS_ABI_VERSION 1
+#define B200GS_ABI_VERSION 2
 #define B200GS_MAX_VIEWS 64 /* per call; callers chunk larger batches */
 
 typedef enum b200gs_status {
@@ -60,6 +60,9 @@ typedef struct b200gs_params {
     float scale_modifier;
     const float *tanfovx;   /* host, [V] */
     const float *tanfovy;   /* host, [V] */
+    int32_t means3D_per_view; /* 0: means3D is [P,3], shared by all views (SDS batch).  1: means3D is [V,P,3] -- every
+                               * view has its own positions, everything else shared: the animation frame batch
+                               * (animation.py:383-403 moves only xyz between frames).  dL_dmeans3D then is [V,P,3]. */
 } b200gs_params;
 
 /* ---- buffer sizing (bytes).  The caller owns three opaque state buffers, exactly as upstream's
@@ -72,7 +75,7 @@ size_t b200gs_backward_scratch_bytes(int32_t P, int32_t n_views);
 /*
  * Forward: preprocess (cull, project, 3D->2D covariance, SH) -> tile binning (scan, key emit, depth sort,
  * tile ranges) -> front-to-back alpha blend.  Replaces rasterize_gaussians.
- *   means3D [P,3]; exactly one of shs [P,M,3] | colors_precomp [P,3]; opacities [P] (post-sigmoid);
+ *   means3D [P,3] (or [V,P,3], see means3D_per_view); exactly one of shs [P,M,3] | colors_precomp [P,3]; opacities [P] (post-sigmoid);
  *   exactly one of (scales [P,3] post-exp AND rotations [P,4] (w,x,y,z)) | cov3D_precomp [P,6];
  *   bg [3]; viewmatrix [V,16]; projmatrix [V,16]; campos [V,3].
  * Outputs: out_color [V,3,H,W]; out_depth [V,1,H,W]; out_alpha [V,1,H,W]; radii [V,P] int32.
@@ -96,7 +99,7 @@ int b200gs_forward(const b200gs_params *prm,
  * buffers written by the matching b200gs_forward call (same prm, same inputs).
  *   dL_dcolor [V,3,H,W]; dL_ddepth [V,1,H,W]; dL_dalpha [V,1,H,W]  (any may be NULL = zero).
  * Gradient outputs (overwritten, not accumulated).  Parameter gradients are summed over the V views:
- *   dL_dmeans3D [P,3]; dL_dmeans2D [V,P,3] (xy in NDC units, z = 0: the densification signal,
+ *   dL_dmeans3D [P,3] (per-view means: [V,P,3], not summed); dL_dmeans2D [V,P,3] (xy in NDC units, z = 0: the densification signal,
  *   GaussianDreamer.py:385-391); dL_dsh [P,M,3] | dL_dcolors [P,3]; dL_dopacity [P];
  *   dL_dscales [P,3] + dL_drots [P,4] | dL_dcov3D [P,6].
  */
@@ -115,6 +118,17 @@ int b200gs_backward(const b200gs_params *prm,
 /* Frustum test only (upstream markVisible): present[i] = 1 if p_view.z > 0.2 for view 0.  positions [P,3]. */
 int b200gs_mark_visible(int32_t P, const float *positions, const float *viewmatrix, const float *projmatrix,
                         uint8_t *present, void *stream);
+
+/* ---- animation frame path (reference animation.py) --------------------------------------------------------------
+ * Re-attachment of the Gaussians to a re-posed body mesh, for n_frames poses at once (animation.py:383-403 does one
+ * frame per call in numpy): xyz_out[f,i] = u*v0 + v*v1 + w*v2 + dist[i] * unit_normal(face), face = faces[mapping_face[i]].
+ *   vertices [n_frames, n_verts, 3]; faces [n_faces,3] int32; mapping_face [P] int32; mapping_uvw [P,3]; mapping_dist [P];
+ *   xyz_out [n_frames, P, 3] -- feed it to b200gs_forward with means3D_per_view = 1. */
+int b200gs_reattach(int32_t P, int32_t n_frames, int32_t n_verts, int32_t n_faces, const float *vertices, const int32_t *faces,
+                    const int32_t *mapping_face, const float *mapping_uvw, const float *mapping_dist, float *xyz_out, void *stream);
+/* clamp(color,0,1) (gs_renderer.py:1017) then CHW float -> HWC uint8 by truncation of x*255 (animation.py:1011).
+ *   color [n_frames,3,H,W] -> out [n_frames,H,W,3] uint8 */
+int b200gs_pack_frames_u8(const float *color, uint8_t *out, int32_t image_height, int32_t image_width, int32_t n_frames, void *stream);
 
 /* ---- introspection of the state buffers, for parity tests (tile/sort indices must match bit-for-bit) ------- */
 typedef struct b200gs_state_view {
