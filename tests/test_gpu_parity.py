@@ -246,3 +246,27 @@ def test_mark_visible():
     m = inp["means3D"]
     z = (V[2] * m[:, 0] + V[6] * m[:, 1]) + V[10] * m[:, 2] + V[14]
     assert (vis == (z > 0.2)).mean() > 0.999
+
+
+def test_real_scene_512_config2():
+    """BASELINE config 2 in miniature: the reference's own scene (a seed-0 8k subsample of content/sample.ply: real
+    anisotropy / opacity statistics; fixture tests/golden/sample_ply_8k.npz), eval-orbit camera, 512x512, fwd+bwd."""
+    import os
+    from humangaussian_b200.cameras import Camera, orbit_c2w
+    from util import ROOT
+    c = np.load(os.path.join(ROOT, "tests", "golden", "sample_ply_8k.npz"))
+    xyz = np.stack([c["x"], c["y"], c["z"]], 1)
+    sc = (np.exp(np.stack([c["scale_0"], c["scale_1"], c["scale_2"]], 1)) * 4.0).astype(np.float32)
+    q = np.stack([c["rot_0"], c["rot_1"], c["rot_2"], c["rot_3"]], 1)
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    op = (1 / (1 + np.exp(-c["opacity"]))).astype(np.float32)
+    sh = np.stack([c["f_dc_0"], c["f_dc_1"], c["f_dc_2"]], 1)[:, None, :].astype(np.float32)
+    cam = Camera(orbit_c2w(15.0, 0.0, 2.0), math.radians(70), 512, 512)
+    inp = dict(means3D=xyz.astype(np.float32), opacities=op, shs=sh, scales=sc, rotations=q, sh_degree=0,
+               viewmatrix=cam.world_view_transform.numpy(), projmatrix=cam.full_proj_transform.numpy(), campos=cam.camera_center.numpy(),
+               bg=np.zeros(3, np.float32), image_height=512, image_width=512, tanfovx=math.tan(cam.FoVx / 2), tanfovy=math.tan(cam.FoVy / 2),
+               scale_modifier=1.0)
+    o_out, o_st, gimg, o_grads = _oracle(inp, 9)
+    assert o_st["num_rendered"] > 20000 and (o_out[1] > 0).all()
+    _check_forward_state(inp, o_out, o_st)
+    _check_backward(inp, o_out, gimg, o_grads)
