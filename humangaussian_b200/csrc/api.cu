@@ -108,6 +108,8 @@ int b200gs_forward(const b200gs_params *prm, const float *means3D, const float *
 
     if (P == 0) { // empty scene: background only
         CK(cudaMemsetAsync(bb + BL.ranges, 0, (size_t)gx * gy * V * 8, st), "memset ranges");
+        int nl0 = 0;
+        if (launch_binning(nullptr, nullptr, nullptr, 0, V, gx, gy, 0, bb, BL, st, &nl0)) return cuda_fail(cudaGetLastError(), "binning");
     } else {
         PreArgs a;
         a.P = P; a.deg = shs ? prm->sh_degree : 0; a.M = prm->sh_coeffs; a.H = H; a.W = W; a.grid_x = gx; a.grid_y = gy;
@@ -146,6 +148,7 @@ int b200gs_forward(const b200gs_params *prm, const float *means3D, const float *
     BlendArgs b;
     b.H = H; b.W = W; b.grid_x = gx; b.grid_y = gy; b.V = V; b.P = P;
     b.ranges = (const uint2 *)(bb + BL.ranges); b.point_list = (const uint32_t *)(bb + BL.vals_out);
+    b.tile_order = (const uint32_t *)(bb + BL.tile_order);
     b.recs = (const GeomRec *)(gb + GL.recs); b.bg = bg;
     b.final_T = (float *)(ib + IL.final_T); b.n_contrib = (uint32_t *)(ib + IL.n_contrib);
     b.out_color = out_color; b.out_depth = out_depth; b.out_alpha = out_alpha;
@@ -187,6 +190,7 @@ int b200gs_backward(const b200gs_params *prm, const float *means3D, const float 
     BlendBwdArgs b;
     b.H = H; b.W = W; b.grid_x = gx; b.grid_y = gy; b.V = V; b.P = P;
     b.ranges = (const uint2 *)(bb + BL.ranges); b.point_list = (const uint32_t *)(bb + BL.vals_out);
+    b.tile_order = (const uint32_t *)(bb + BL.tile_order);
     b.recs = (const GeomRec *)(gb + GL.recs); b.bg = bg;
     b.final_T = (const float *)(ib + IL.final_T); b.n_contrib = (const uint32_t *)(ib + IL.n_contrib);
     b.dL_dcolor = dL_dcolor; b.dL_ddepth = dL_ddepth; b.dL_dalpha = dL_dalpha;

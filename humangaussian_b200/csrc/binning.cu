@@ -51,6 +51,8 @@ BinLayout binning_layout(int64_t capacity, int ntiles_total, int64_t n_vp)
     L.dkeys_out = o; o += gs_align(nvp * 8);
     L.order_in = o; o += gs_align(nvp * 4);
     L.order = o; o += gs_align(nvp * 4);
+    L.tile_order = o; o += gs_align((size_t)ntiles_total * 4);
+    L.tile_order_cnt = o; o += gs_align(64 * 4);
     const int tbits = bits_for((uint64_t)ntiles_total) > 0 ? bits_for((uint64_t)ntiles_total) : 1;
     const size_t s_depth = sort_scratch_bytes((int64_t)nvp, D_TILE, 1 << D_BITS, MAXP);
     const size_t s_tile = sort_scratch_bytes((int64_t)cap, T_TILE, 1 << T_BITS, (tbits + T_BITS - 1) / T_BITS);
@@ -153,6 +155,46 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t *__rest
     if (j == D - 1) ranges[t].y = (uint32_t)D;
 }
 
+// ---- launch order of the tiles: longest list first (LPT).  One view is otherwise bounded by its heaviest tiles being
+// dispatched in the middle of the grid; results do not depend on this order.  Buckets = floor(log2(length)) + 1.
+__global__ void __launch_bounds__(256) tile_bucket_count_kernel(const uint2 *__restrict__ ranges, int n, uint32_t *__restrict__ cnt)
+{
+    __shared__ uint32_t sh[32];
+    if (threadIdx.x < 32) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) {
+        const uint2 r = ranges[t];
+        atomicAdd(&sh[32 - __clz(r.y - r.x)], 1u); // length 0 -> bucket 0, 1 -> 1, 2..3 -> 2, ...
+    }
+    __syncthreads();
+    if (threadIdx.x < 32 && sh[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], sh[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) tile_bucket_scatter_kernel(const uint2 *__restrict__ ranges, int n, uint32_t *__restrict__ cnt /* [0,32): counts, [32,64): cursors */,
+                                                                   uint32_t *__restrict__ order)
+{
+    __shared__ uint32_t s_base[32], s_local[32];
+    if (threadIdx.x < 32) s_local[threadIdx.x] = 0;
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = 0;
+    uint32_t my = 0;
+    if (t < n) {
+        const uint2 r = ranges[t];
+        b = 32 - __clz(r.y - r.x);
+        my = atomicAdd(&s_local[b], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        // descending buckets: start of bucket k = sum of counts of buckets > k ; claim this CTA's slice with one atomic
+        uint32_t start = 0;
+        for (int k = 31; k > (int)threadIdx.x; k--) start += cnt[k];
+        s_base[threadIdx.x] = s_local[threadIdx.x] ? start + atomicAdd(&cnt[32 + threadIdx.x], s_local[threadIdx.x]) : 0u;
+    }
+    __syncthreads();
+    if (t < n) order[s_base[b] + my] = (uint32_t)t;
+}
+
 // After this call the sorted tile keys are at bin_base+L.keys_out and the point list at bin_base+L.vals_out
 // (a device-to-device copy fixes the parity when the number of passes is even).
 int launch_binning(const uint32_t *order_sorted, const uint2 *rects, const uint32_t *offsets_sorted, int P, int V, int grid_x, int grid_y,
@@ -164,7 +206,15 @@ int launch_binning(const uint32_t *order_sorted, const uint2 *rects, const uint3
     uint32_t *vals_in = (uint32_t *)(bin_base + L.vals_in), *vals_out = (uint32_t *)(bin_base + L.vals_out);
     uint2 *ranges = (uint2 *)(bin_base + L.ranges);
     cudaMemsetAsync(ranges, 0, (size_t)ntiles * V * 8, st);
-    if (D == 0) return 0;
+    uint32_t *tile_order = (uint32_t *)(bin_base + L.tile_order), *tcnt = (uint32_t *)(bin_base + L.tile_order_cnt);
+    const int nt_all = ntiles * V;
+    if (D == 0) { // every list is empty: identity order
+        cudaMemsetAsync(tcnt, 0, 64 * 4, st);
+        tile_bucket_count_kernel<<<(nt_all + 255) / 256, 256, 0, st>>>(ranges, nt_all, tcnt);
+        tile_bucket_scatter_kernel<<<(nt_all + 255) / 256, 256, 0, st>>>(ranges, nt_all, tcnt, tile_order);
+        *n_launches += 2;
+        return 0;
+    }
     if (D >= ((int64_t)1 << 30)) return -3; // look-back status words carry 30-bit counts
     const int nbits = bits_for((uint64_t)ntiles * V) > 0 ? bits_for((uint64_t)ntiles * V) : 1;
     const int npass = (nbits + T_BITS - 1) / T_BITS;
@@ -176,7 +226,10 @@ int launch_binning(const uint32_t *order_sorted, const uint2 *rects, const uint3
     if (radix_sort_pairs<uint32_t, T_BITS, T_IPT>(k0, k1, v0, v1, D, nbits, bin_base + L.temp, L.temp_bytes, &ks, &vs, st, n_launches)) return -2;
     if (ks != keys_out || vs != vals_out) return -4;
     tile_ranges_kernel<<<(unsigned)((D + 255) / 256), 256, 0, st>>>(keys_out, D, ranges);
-    *n_launches += 2;
+    cudaMemsetAsync(tcnt, 0, 64 * 4, st);
+    tile_bucket_count_kernel<<<(nt_all + 255) / 256, 256, 0, st>>>(ranges, nt_all, tcnt);
+    tile_bucket_scatter_kernel<<<(nt_all + 255) / 256, 256, 0, st>>>(ranges, nt_all, tcnt, tile_order);
+    *n_launches += 4;
     return 0;
 }
 

@@ -60,7 +60,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_fwd_kernel(BlendArgs
 
     const int ntiles = a.grid_x * a.grid_y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x / CTAS_PER_TILE, v = blockIdx.y;
+    // CTAs are dispatched in blockIdx order; tile_order lists (view, tile) pairs longest list first, so the heavy
+    // tiles of a launch start first and the short ones fill in behind them (LPT schedule)
+    const uint32_t vt = a.tile_order[blockIdx.x / CTAS_PER_TILE];
+    const int v = (int)(vt / (uint32_t)ntiles), tile = (int)(vt % (uint32_t)ntiles);
     const int patch = (blockIdx.x % CTAS_PER_TILE) * WARPS_PER_CTA + warp; // 0..7: bit0 = x half, bits 1-2 = row band
     const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
     const int x0 = tile_x * GS_TILE + (patch & 1) * 8, y0 = tile_y * GS_TILE + (patch >> 1) * 4;
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_fwd_kernel(BlendArgs
 
 void launch_blend_fwd(const BlendArgs &a, cudaStream_t st)
 {
-    dim3 grid(a.grid_x * a.grid_y * CTAS_PER_TILE, a.V);
+    const unsigned grid = (unsigned)(a.grid_x * a.grid_y * CTAS_PER_TILE * a.V);
     blend_fwd_kernel<<<grid, 32 * WARPS_PER_CTA, 0, st>>>(a);
 }
 
@@ -201,7 +204,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
 
     const int ntiles = a.grid_x * a.grid_y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x / CTAS_PER_TILE, v = blockIdx.y;
+    // CTAs are dispatched in blockIdx order; tile_order lists (view, tile) pairs longest list first, so the heavy
+    // tiles of a launch start first and the short ones fill in behind them (LPT schedule)
+    const uint32_t vt = a.tile_order[blockIdx.x / CTAS_PER_TILE];
+    const int v = (int)(vt / (uint32_t)ntiles), tile = (int)(vt % (uint32_t)ntiles);
     const int patch = (blockIdx.x % CTAS_PER_TILE) * WARPS_PER_CTA + warp; // 0..7: bit0 = x half, bits 1-2 = row band
     const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
     const int x0 = tile_x * GS_TILE + (patch & 1) * 8, y0 = tile_y * GS_TILE + (patch >> 1) * 4;
@@ -323,7 +329,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
 
 void launch_blend_bwd(const BlendBwdArgs &a, cudaStream_t st)
 {
-    dim3 grid(a.grid_x * a.grid_y * CTAS_PER_TILE, a.V);
+    const unsigned grid = (unsigned)(a.grid_x * a.grid_y * CTAS_PER_TILE * a.V);
     blend_bwd_kernel<<<grid, 32 * WARPS_PER_CTA, 0, st>>>(a);
 }
 

@@ -36,6 +36,7 @@ struct PreBwdArgs {
 
 struct BlendArgs {
     int H, W, grid_x, grid_y, V, P;
+    const uint32_t *tile_order; // [V*tiles] (view*tiles + tile) sorted by descending list length: longest first
     const uint2 *ranges;        // [V*tiles]
     const uint32_t *point_list; // [D] index into recs (= v*P + gaussian)
     const GeomRec *recs;        // [V*P]
@@ -47,6 +48,7 @@ struct BlendArgs {
 
 struct BlendBwdArgs {
     int H, W, grid_x, grid_y, V, P;
+    const uint32_t *tile_order;
     const uint2 *ranges;
     const uint32_t *point_list;
     const GeomRec *recs;
@@ -65,6 +67,7 @@ void launch_mark_visible(int P, const float *pos, const float *V, uint8_t *prese
 struct BinLayout {
     size_t keys_in, keys_out, vals_in, vals_out, ranges; // per-instance tile keys (u32) / record indices (u32), tile ranges
     size_t dkeys_in, dkeys_out, order_in, order;         // per-Gaussian (view|depth) keys (u64) and the depth order (u32)
+    size_t tile_order, tile_order_cnt;                   // launch order of the tiles (longest list first) + 32 bucket counters
     size_t temp, total;
     size_t temp_bytes;
 };

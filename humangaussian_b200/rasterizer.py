@@ -264,6 +264,8 @@ class _RasterizeViews(torch.autograd.Function):
         color, radii, depth, alpha, st = _forward_impl(*args, *camt, tanx, tany, H, W, deg, mod, prefiltered, debug)
         ctx.st, ctx.squeeze = st, squeeze
         ctx.saved = args + camt  # plain references: these are detached copies or the caller's own storage
+        ctx.in_shapes = [None if t is None else t.shape for t in (means3D, means2D, shs, colors_precomp, opacities, scales,
+                                                                  rotations, cov3D_precomp)]
         ctx.mark_non_differentiable(radii)
         if squeeze:
             return color[0], radii[0], depth[0], alpha[0]
@@ -281,7 +283,10 @@ class _RasterizeViews(torch.autograd.Function):
             d_means2D = d_means2D[0]
         ctx.st = None
         ctx.saved = None
-        return d_means3D, d_means2D, d_sh, d_col, d_op, d_sc, d_rot, d_cov, None, None
+        # gradients take the shape the caller passed (e.g. opacities [P] or [P,1])
+        grads = [g if (g is None or shp is None) else g.reshape(shp)
+                 for g, shp in zip((d_means3D, d_means2D, d_sh, d_col, d_op, d_sc, d_rot, d_cov), ctx.in_shapes)]
+        return (*grads, None, None)
 
 
 class GaussianRasterizationSettings(NamedTuple):
