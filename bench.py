@@ -347,8 +347,16 @@ def run_b200(args):
                             "frac_of_hbm_peak": bytes_stage[k] / (per * 1e-3) / 1e9 / peak}
         dom = max(table, key=lambda k: table[k]["ms_per_launch_set"])
         total_bytes = sum(bytes_stage.values())
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes per launch of the dominant kernel, from the committed ncu capture (per view x views of this launch)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = int(tj[dom]["dram_bytes_per_view"] * V)
+            traffic_src = tj[dom]["capture"]
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": table[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": table[dom]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                "frac": table[dom]["frac_of_hbm_peak"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_stage[dom],
                 "note": "blend kernels are FP32-issue/atomic bound, not HBM bound (SURVEY.md 8d caveat); see profiles/ for ncu pipe utilisation",
                 "whole_step": {"algorithmic_bytes": total_bytes, "achieved_gbs": total_bytes / (ms_step * 1e-3) / 1e9,
                                "frac": total_bytes / (ms_step * 1e-3) / 1e9 / peak},
