@@ -276,6 +276,21 @@ int b200gs_profile_read(double *ms_per_stage, int64_t *calls_per_stage, int32_t 
     return B200GS_OK;
 }
 
+size_t b200gs_knn_scratch_bytes(int32_t P) { return knn_scratch_bytes(P); }
+
+int b200gs_dist2_knn3(int32_t P, const float *points, float *mean_dist2, void *scratch, size_t scratch_bytes, void *stream)
+{
+    if (P < 0 || !points || !mean_dist2 || !scratch) return B200GS_E_ARGS;
+    if (P < 4) return B200GS_E_RANGE; // needs 3 neighbours besides the point itself
+    int nl = 0;
+    const int rc = launch_knn3(P, points, mean_dist2, (char *)scratch, scratch_bytes, (cudaStream_t)stream, &nl);
+    if (rc == -1) return B200GS_E_BUFFER;
+    if (rc) return B200GS_E_RANGE;
+    g_launches += nl;
+    CK(cudaGetLastError(), "knn launch");
+    return B200GS_OK;
+}
+
 int b200gs_reattach(int32_t P, int32_t n_frames, int32_t n_verts, int32_t n_faces, const float *vertices, const int32_t *faces,
                     const int32_t *mapping_face, const float *mapping_uvw, const float *mapping_dist, float *xyz_out, void *stream)
 {

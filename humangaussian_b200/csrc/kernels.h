@@ -89,3 +89,7 @@ void launch_test_exp(const float *x, float *y, int64_t n, cudaStream_t st);
 void launch_reattach(int P, int n_frames, int n_verts, const float *vertices, const int32_t *faces, const int32_t *map_face,
                      const float *map_uvw, const float *map_dist, float *xyz, cudaStream_t st);
 void launch_pack_u8(const float *color, uint8_t *out, int H, int W, int n_frames, cudaStream_t st);
+
+// 3-nearest-neighbour mean squared distance (knn.cu)
+size_t knn_scratch_bytes(int P);
+int launch_knn3(int P, const float *pts, float *mean_d2, char *scratch, size_t scratch_bytes, cudaStream_t st, int *n_launches);

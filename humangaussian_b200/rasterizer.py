@@ -49,7 +49,8 @@ _lib = None
 EXPORTS = ["b200gs_forward", "b200gs_backward", "b200gs_mark_visible", "b200gs_describe_state", "b200gs_test_exp",
            "b200gs_geom_bytes", "b200gs_image_bytes", "b200gs_binning_bytes", "b200gs_backward_scratch_bytes",
            "b200gs_last_cuda_error", "b200gs_abi_version", "b200gs_launch_count", "b200gs_profile_enable", "b200gs_profile_read",
-           "b200gs_test_sort_pairs", "b200gs_test_sort_scratch_bytes", "b200gs_reattach", "b200gs_pack_frames_u8"]
+           "b200gs_test_sort_pairs", "b200gs_test_sort_scratch_bytes", "b200gs_reattach", "b200gs_pack_frames_u8",
+           "b200gs_knn_scratch_bytes", "b200gs_dist2_knn3"]
 STAGES = ["preprocess_fwd", "scan", "binning", "blend_fwd", "blend_bwd", "preprocess_bwd"]
 
 
@@ -87,6 +88,9 @@ def load_library():
     L.b200gs_reattach.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.b200gs_pack_frames_u8.restype = C.c_int
     L.b200gs_pack_frames_u8.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.b200gs_knn_scratch_bytes.restype = sz; L.b200gs_knn_scratch_bytes.argtypes = [i32]
+    L.b200gs_dist2_knn3.restype = C.c_int
+    L.b200gs_dist2_knn3.argtypes = [i32, vp, vp, vp, sz, vp]
     L.b200gs_last_cuda_error.restype = C.c_char_p
     L.b200gs_launch_count.restype = i64
     L.b200gs_profile_enable.restype = None; L.b200gs_profile_enable.argtypes = [C.c_int]
@@ -427,6 +431,20 @@ def device_sort_pairs(keys: torch.Tensor, vals: torch.Tensor, nbits: int):
         _check(L.b200gs_test_sort_pairs(_ptr(ka), _ptr(kb), _ptr(va), _ptr(vb), n, int(nbits), _ptr(scratch), scratch.numel(),
                                         C.byref(in_b), _stream(ka.device)), "test_sort_pairs")
     return (kb, vb) if in_b.value else (ka, va)
+
+
+def distCUDA2(points: torch.Tensor) -> torch.Tensor:
+    """Mean squared distance to the 3 nearest neighbours, per point (the reference's simple_knn._C.distCUDA2)."""
+    L = load_library()
+    pts = _f32c(points)
+    if pts.device.type != "cuda":
+        raise RuntimeError("b200gs: tensors must live on a CUDA device (there is no CPU path)")
+    P = pts.shape[0]
+    out = torch.empty(P, dtype=torch.float32, device=pts.device)
+    scratch = torch.empty(L.b200gs_knn_scratch_bytes(P), dtype=torch.uint8, device=pts.device)
+    with torch.cuda.device(pts.device):
+        _check(L.b200gs_dist2_knn3(P, _ptr(pts), _ptr(out), _ptr(scratch), scratch.numel(), _stream(pts.device)), "dist2_knn3")
+    return out
 
 
 def device_exp(x: torch.Tensor) -> torch.Tensor:

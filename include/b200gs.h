@@ -130,6 +130,13 @@ int b200gs_reattach(int32_t P, int32_t n_frames, int32_t n_verts, int32_t n_face
  *   color [n_frames,3,H,W] -> out [n_frames,H,W,3] uint8 */
 int b200gs_pack_frames_u8(const float *color, uint8_t *out, int32_t image_height, int32_t image_width, int32_t n_frames, void *stream);
 
+/* ---- scene initialisation helper (reference: simple_knn._C.distCUDA2, gaussiansplatting/submodules/simple-knn/
+ * simple_knn.cu:63-221 via spatial.cu:15-26; callers scene/gaussian_model.py:134, gs_renderer.py:386-389) ----------
+ * mean_dist2[i] = mean of the squared distances from points[i] to its 3 nearest other points (exact kNN).
+ *   points [P,3]; mean_dist2 [P]; scratch of b200gs_knn_scratch_bytes(P) bytes; P >= 4. */
+size_t b200gs_knn_scratch_bytes(int32_t P);
+int b200gs_dist2_knn3(int32_t P, const float *points, float *mean_dist2, void *scratch, size_t scratch_bytes, void *stream);
+
 /* ---- introspection of the state buffers, for parity tests (tile/sort indices must match bit-for-bit) ------- */
 typedef struct b200gs_state_view {
     const void *geom_records;     /* [V*P] x 48 B: px,py,hx,hy | conicA,conicB,conicC,opacity | r,g,b,depth */
