@@ -226,3 +226,21 @@ def with_sh_degree(p: GaussianParams, sh_degree, seed=0, std=0.1):
     have = p.features_rest.shape[1]
     rest[:, :have] = p.features_rest
     return GaussianParams(p.xyz, p.features_dc, rest, p.scaling, p.rotation, p.opacity, sh_degree)
+
+
+def params_from_pcd(points, colors, sh_degree=0, device="cuda"):
+    """GaussianModel.create_from_pcd (gaussiansplatting/scene/gaussian_model.py:124-147): DC feature = RGB2SH(colour),
+    higher SH bands 0, isotropic log-scale = log sqrt(clamp_min(mean squared distance to the 3 nearest neighbours,
+    1e-7)), identity quaternion, opacity = inverse_sigmoid(0.1).  The neighbour distances come from this repo's
+    distCUDA2 kernel (the reference calls simple_knn._C.distCUDA2)."""
+    from .rasterizer import distCUDA2
+    pts = torch.as_tensor(points, dtype=torch.float32, device=device)
+    col = torch.as_tensor(colors, dtype=torch.float32, device=device)
+    P, K = pts.shape[0], (sh_degree + 1) ** 2
+    dist2 = torch.clamp_min(distCUDA2(pts), 0.0000001)
+    scaling = torch.log(torch.sqrt(dist2))[..., None].repeat(1, 3)
+    rotation = torch.zeros(P, 4, device=device)
+    rotation[:, 0] = 1
+    opacity = torch.full((P, 1), float(np.log(0.1 / 0.9)), dtype=torch.float32, device=device)
+    return GaussianParams(pts, RGB2SH(col)[:, None, :].contiguous(), torch.zeros(P, K - 1, 3, device=device), scaling, rotation, opacity,
+                          sh_degree)

@@ -35,3 +35,16 @@ def test_duplicate_points_give_zero():
     from simple_knn._C import distCUDA2
     pts = np.tile(np.array([[0.1, 0.2, 0.3]], np.float32), (64, 1))
     assert float(distCUDA2(torch.tensor(pts, device=DEV)).abs().max()) == 0.0
+
+
+def test_params_from_pcd_matches_reference_init():
+    """create_from_pcd (gaussian_model.py:124-147): scales from the 3-NN distances, identity rotations, opacity 0.1."""
+    from humangaussian_b200.scene import params_from_pcd, synthetic_body
+    pts = synthetic_body(20_000, seed=2).xyz.numpy()
+    col = np.random.RandomState(0).rand(20_000, 3).astype(np.float32)
+    p = params_from_pcd(pts, col, sh_degree=1, device=DEV)
+    want_scale = np.log(np.sqrt(np.maximum(_exact(pts), 1e-7)))
+    assert np.allclose(p.scaling.cpu().numpy(), want_scale[:, None].repeat(3, 1), atol=2e-4)
+    assert torch.allclose(p.get_opacity, torch.full_like(p.get_opacity, 0.1), atol=1e-6)
+    assert torch.equal(p.get_rotation, torch.tensor([1.0, 0, 0, 0], device=DEV).expand(20_000, 4))
+    assert np.allclose(p.features_dc.cpu().numpy()[:, 0], (col - 0.5) / 0.28209479177387814, atol=1e-6) and p.features_rest.shape == (20_000, 3, 3)
