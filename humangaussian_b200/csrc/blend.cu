@@ -245,9 +245,15 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
     const float bg_dot = a.bg[0] * gC0 + a.bg[1] * gC1 + a.bg[2] * gC2;
     const int slot = slot_of_lane(lane);
     float *const sg_slot = reinterpret_cast<float *>(a.sgrad) + (slot >= 0 ? slot : 0); // this lane's column of ScreenGrad
+    // Per-pixel state of the back-to-front replay.  Upstream keeps five "accumulated colour behind" recurrences
+    // (r,g,b,depth,alpha), each rec = last_alpha*last_c + (1-last_alpha)*rec, and forms sum_ch (c_ch - rec_ch)*g_ch.
+    // The recurrences are linear with identical coefficients, so their dot product with the pixel's fixed upstream
+    // gradient g = (gC, gD, gA) obeys the SAME (convex, numerically stable) recurrence as ONE scalar:
+    //   cg_j = c_j.gC + depth_j*gD + gA ;   rg <- last_alpha*last_cg + (1-last_alpha)*rg ;
+    //   dL/dalpha_j = T_j*(cg_j - rg) - T_final*(bg.gC)/(1-alpha_j)
     float T = T_final;
-    float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, ld = 0.f;
-    float ac0 = 0.f, ac1 = 0.f, ac2 = 0.f, ad = 0.f, aa = 0.f;
+    const float Kbg = T_final * bg_dot;
+    float rg = 0.f, last_cg = 0.f, last_alpha = 0.f;
 
     // back to front: chunk [hi-32, hi), lane l <-> list position hi-1-l; the next chunk's loads are in flight
     uint32_t id_c = 0;
@@ -275,7 +281,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
         if (b == 0u) continue;
         if (hit) {
             const int s = __popc(b & lt);
-            sl.rec[3 * s] = g0_h;
+            // the support box has done its job: its two slots now carry -A and -C (= 2A', 2C') for the mean-gradient sums
+            sl.rec[3 * s] = make_float4(g0_h.x, g0_h.y, -g1.x, -g1.z);
             sl.rec[3 * s + 1] = make_float4(fmul(-0.5f, g1.x), -g1.y, fmul(-0.5f, g1.z), g1.w);
             sl.rec[3 * s + 2] = g2;
             sl.pos[s] = (uint32_t)(hi - 1 - lane);
@@ -295,31 +302,23 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
             float q = 0.f, w = 0.f;
             if (contrib) {
                 const float4 q2 = sl.rec[3 * i + 2];
+                const float cg = fmaf(q2.x, gC0, fmaf(q2.y, gC1, fmaf(q2.z, gC2, fmaf(q2.w, gD, gA))));
                 const float one_m_a = 1.0f - alpha;
                 float inv; // 1/(1-alpha), 1-alpha in [0.01, 1): the single-instruction MUFU reciprocal (<= 1 ulp) suffices
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(one_m_a));
                 T = T * inv;
                 w = alpha * T;
-                ac0 = fmaf(last_alpha, lc0 - ac0, ac0); lc0 = q2.x;
-                ac1 = fmaf(last_alpha, lc1 - ac1, ac1); lc1 = q2.y;
-                ac2 = fmaf(last_alpha, lc2 - ac2, ac2); lc2 = q2.z;
-                ad = fmaf(last_alpha, ld - ad, ad); ld = q2.w;
-                aa = fmaf(last_alpha, 1.0f - aa, aa);
-                float dL_dalpha = (q2.x - ac0) * gC0;
-                dL_dalpha = fmaf(q2.y - ac1, gC1, dL_dalpha);
-                dL_dalpha = fmaf(q2.z - ac2, gC2, dL_dalpha);
-                dL_dalpha = fmaf(q2.w - ad, gD, dL_dalpha);
-                dL_dalpha = fmaf(1.0f - aa, gA, dL_dalpha);
-                dL_dalpha *= T;
+                rg = fmaf(last_alpha, last_cg - rg, rg);
+                last_cg = cg;
                 last_alpha = alpha;
-                dL_dalpha = fmaf(-T_final * inv, bg_dot, dL_dalpha);
+                const float dL_dalpha = fmaf(T, cg - rg, -(Kbg * inv));
                 q = G * dL_dalpha;
             }
             // Mx = -sum q (A dx + B dy), My = -sum q (C dy + B dx): formed per pixel (not from the moments sum q dx,
             // sum q dy) so that the A.Sx + B.Sy cancellation of elongated Gaussians is not amplified by rounding.
             const float qx = q * dx, qy = q * dy;
-            const float mx = q * fmaf(q1.y, dy, (q1.x + q1.x) * dx);
-            const float my = q * fmaf(q1.y, dx, (q1.z + q1.z) * dy);
+            const float mx = q * fmaf(q1.y, dy, g0.z * dx);
+            const float my = q * fmaf(q1.y, dx, g0.w * dy);
             const float e = butterfly10(q, mx, my, qx * dx, qx * dy, qy * dy, w * gC0, w * gC1, w * gC2, w * gD, lane);
             if (slot >= 0) atomicAdd(sg_slot + 12 * (size_t)sl.id[i], e);
         }
