@@ -81,8 +81,11 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(hi, ma
 // 48-byte record per view.  Per step this reads P*(44+12K) bytes instead of V times that.
 // DEG = -1: colours are given (colors_precomp), no SH.
 // ------------------------------------------------------------------------------------------------
+#ifndef PFWD_MIN_BLOCKS
+#define PFWD_MIN_BLOCKS 3 // swept on B200: 80 registers
+#endif
 template <int DEG>
-__global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreArgs a, int nviews)
+__global__ void __launch_bounds__(256, PFWD_MIN_BLOCKS) preprocess_fwd_kernel(PreArgs a, int nviews)
 {
     constexpr int NB = DEG < 0 ? 1 : (DEG + 1) * (DEG + 1);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -277,8 +280,11 @@ void launch_mark_visible(int P, const float *pos, const float *V, uint8_t *prese
 // B2 + B3: one thread per Gaussian, loops over the views of the batch and SUMS parameter gradients
 // (deterministic: no atomics at the parameter level).  Plain float arithmetic (tolerance-compared).
 // ------------------------------------------------------------------------------------------------
+#ifndef PBWD_MIN_BLOCKS
+#define PBWD_MIN_BLOCKS 4 // swept on B200: 128 registers (a few spills) beats 227 registers at 8 warps/SM
+#endif
 template <int DEG>
-__global__ void __launch_bounds__(128) preprocess_bwd_kernel(PreBwdArgs a)
+__global__ void __launch_bounds__(128, PBWD_MIN_BLOCKS) preprocess_bwd_kernel(PreBwdArgs a)
 {
     constexpr int nb = DEG < 0 ? 1 : (DEG + 1) * (DEG + 1);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
