@@ -123,5 +123,43 @@ def sample_orbit_cameras(n, height, width, seed=0, elevation_range=(-30.0, 30.0)
     az = (torch.rand(n, generator=g) + torch.arange(n)) / n * (azimuth_range[1] - azimuth_range[0]) + azimuth_range[0]
     dist = torch.rand(n, generator=g) * (distance_range[1] - distance_range[0]) + distance_range[0]
     fovy = torch.rand(n, generator=g) * (fovy_range[1] - fovy_range[0]) + fovy_range[0]
-    return [Camera(orbit_c2w(float(el[i]), float(az[i]), float(dist[i])), math.radians(float(fovy[i])),
-                   height, width, device=device) for i in range(n)]
+    # matrices are built on the host (tiny 4x4 work) and moved once: building them on the GPU costs ~10 launches per camera
+    cams = [Camera(orbit_c2w(float(el[i]), float(az[i]), float(dist[i])), math.radians(float(fovy[i])), height, width, device="cpu")
+            for i in range(n)]
+    if str(device) != "cpu":
+        for c in cams:
+            c.world_view_transform = c.world_view_transform.to(device)
+            c.projection_matrix = c.projection_matrix.to(device)
+            c.full_proj_transform = c.full_proj_transform.to(device)
+            c.camera_center = c.camera_center.to(device)
+    return cams
+
+class CameraBatch:
+    """All cameras of an SDS step at once: the arithmetic of `Camera` (scene/cameras.py:17-54), batched over B poses
+    (three batched tensor ops instead of ~6 small kernels per camera) -- SURVEY.md 8f-1's "camera-matrix construction".
+
+    c2w [B,4,4], fovy [B] (radians).  Attributes: world_view_transform [B,4,4], full_proj_transform [B,4,4],
+    camera_center [B,3], tanfovx / tanfovy (lists of B floats), image_height, image_width -- what rasterize_views takes."""
+
+    def __init__(self, c2w, fovy, height, width, device="cpu", znear=0.01, zfar=100.0):
+        c2w = torch.as_tensor(c2w, dtype=torch.float32).cpu().clone()
+        fovy = [float(f) for f in torch.as_tensor(fovy).reshape(-1).tolist()]
+        B = c2w.shape[0]
+        if len(fovy) != B:
+            raise ValueError("one fovy per pose")
+        w2c = torch.inverse(c2w)
+        w2c[:, 1:3, :3] *= -1
+        w2c[:, :3, 3] *= -1
+        wvt = w2c.transpose(1, 2).contiguous()
+        fovx = [focal2fov(fov2focal(fy, height), width) for fy in fovy]
+        proj = torch.stack([getProjectionMatrix(znear, zfar, fx, fy).transpose(0, 1) for fx, fy in zip(fovx, fovy)])
+        self.world_view_transform = wvt.to(device)
+        self.full_proj_transform = torch.bmm(wvt, proj).contiguous().to(device)
+        self.camera_center = torch.inverse(wvt)[:, 3, :3].contiguous().to(device)
+        self.FoVx, self.FoVy = fovx, fovy
+        self.tanfovx = [math.tan(f * 0.5) for f in fovx]
+        self.tanfovy = [math.tan(f * 0.5) for f in fovy]
+        self.image_height, self.image_width = int(height), int(width)
+
+    def __len__(self):
+        return self.world_view_transform.shape[0]

@@ -158,3 +158,18 @@ def test_real_scene_subsample_renders_and_sorts():
     assert (r[nonempty, 1] - r[nonempty, 0]).sum() == D
     assert np.isfinite(col).all() and alp.max() <= 1.0 + 1e-5 and alp.max() > 0.5
     assert (st["depths"][radii > 0] > 0.2).all()
+
+
+def test_camera_batch_equals_per_camera():
+    from humangaussian_b200.cameras import Camera, CameraBatch, orbit_c2w, sample_orbit_cameras
+    specs = [(15.0, 0.0, 2.0, 70.0), (-20.0, 135.0, 1.6, 45.0), (5.0, -90.0, 1.9, 55.0), (29.0, 179.0, 1.5, 40.0)]
+    c2w = torch.stack([orbit_c2w(e, a, d) for e, a, d, _ in specs])
+    fovy = [math.radians(f) for *_, f in specs]
+    cb = CameraBatch(c2w, fovy, 512, 384)
+    for i, (e, a, d, f) in enumerate(specs):
+        c = Camera(orbit_c2w(e, a, d), math.radians(f), 512, 384)
+        assert torch.allclose(cb.world_view_transform[i], c.world_view_transform, atol=1e-6)
+        assert torch.allclose(cb.full_proj_transform[i], c.full_proj_transform, atol=1e-6)
+        assert torch.allclose(cb.camera_center[i], c.camera_center, atol=1e-6)
+        assert abs(cb.tanfovx[i] - math.tan(c.FoVx / 2)) < 1e-12 and abs(cb.tanfovy[i] - math.tan(c.FoVy / 2)) < 1e-12
+    assert len(sample_orbit_cameras(3, 64, 64, seed=1)) == 3
