@@ -143,7 +143,7 @@ class CameraBatch:
 
     def __init__(self, c2w, fovy, height, width, device="cpu", znear=0.01, zfar=100.0):
         c2w = torch.as_tensor(c2w, dtype=torch.float32).cpu().clone()
-        fovy = [float(f) for f in torch.as_tensor(fovy).reshape(-1).tolist()]
+        fovy = [float(f) for f in (fovy.reshape(-1).tolist() if torch.is_tensor(fovy) else list(fovy))]
         B = c2w.shape[0]
         if len(fovy) != B:
             raise ValueError("one fovy per pose")
