@@ -142,7 +142,7 @@ int b200gs_forward(const b200gs_params *prm, const float *means3D, const float *
             if (brc == -3) return B200GS_E_RANGE;
             if (brc) return cuda_fail(cudaGetLastError(), "binning");
         }
-        g_launches += nl; // histogram, digit scan, onesweep passes, tile scan, emit, ranges: all ours
+        g_launches += nl; // radix count/scan/scatter passes, tile scan, emit, ranges, tile order: all ours
         // remember where the depth order landed (ping-pong parity) for b200gs_describe_state
     }
     BlendArgs b;

@@ -10,7 +10,7 @@
 //   5. tile ranges from the sorted tile keys
 // Stability of step 4 keeps step 1's (depth, index) order inside every tile, so point_list and ranges are
 // bit-identical to the reference's single 64-bit sort (tests compare them, and the reconstructed 64-bit keys,
-// against the oracle).  The sort and scan primitives are in radix.cuh (onesweep passes with look-back).
+// against the oracle).  The sort (count / scan / ranked-scatter passes) and the look-back scan are in radix.cuh.
 #include "common.cuh"
 #include "kernels.h"
 #include "radix.cuh"
@@ -30,9 +30,9 @@ constexpr int T_BITS = 9, T_IPT = 12, T_TILE = THREADS * T_IPT;   // tile sort: 
 constexpr int MAXP = 5;
 constexpr int SCAN_TILE = THREADS * SCAN_IPT;
 
-static size_t sort_scratch_bytes(int64_t n, int tile, int bins, int max_passes)
+// scratch of one radix sort: digit totals + the [digit][CTA] count matrix (re-used by every pass)
+static size_t sort_scratch_bytes(int64_t n, int tile, int bins)
 {
-    (void)max_passes;
     const size_t nblocks = (size_t)((n + tile - 1) / tile) + 1;
     return gs_align((size_t)bins * 4) + gs_align(nblocks * bins * 4);
 }
@@ -53,9 +53,8 @@ BinLayout binning_layout(int64_t capacity, int ntiles_total, int64_t n_vp)
     L.order = o; o += gs_align(nvp * 4);
     L.tile_order = o; o += gs_align((size_t)ntiles_total * 4);
     L.tile_order_cnt = o; o += gs_align(64 * 4);
-    const int tbits = bits_for((uint64_t)ntiles_total) > 0 ? bits_for((uint64_t)ntiles_total) : 1;
-    const size_t s_depth = sort_scratch_bytes((int64_t)nvp, D_TILE, 1 << D_BITS, MAXP);
-    const size_t s_tile = sort_scratch_bytes((int64_t)cap, T_TILE, 1 << T_BITS, (tbits + T_BITS - 1) / T_BITS);
+    const size_t s_depth = sort_scratch_bytes((int64_t)nvp, D_TILE, 1 << D_BITS);
+    const size_t s_tile = sort_scratch_bytes((int64_t)cap, T_TILE, 1 << T_BITS);
     const size_t s_scan = gs_align(((nvp + SCAN_TILE - 1) / SCAN_TILE + 1) * 8) + 256;
     size_t t = s_depth > s_tile ? s_depth : s_tile;
     t = t > s_scan ? t : s_scan;
@@ -243,4 +242,4 @@ int launch_test_sort32(uint32_t *ka, uint32_t *kb, uint32_t *va, uint32_t *vb, i
     *result_in_b = (ks == kb);
     return rc;
 }
-size_t test_sort32_scratch_bytes(int64_t n) { return sort_scratch_bytes(n, T_TILE, 1 << T_BITS, 4); }
+size_t test_sort32_scratch_bytes(int64_t n) { return sort_scratch_bytes(n, T_TILE, 1 << T_BITS); }

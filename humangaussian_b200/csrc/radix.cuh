@@ -15,7 +15,6 @@ namespace gsradix {
 
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
-constexpr uint32_t FLAG_AGG = 1u << 30, FLAG_PREFIX = 2u << 30, FLAG_MASK = 3u << 30, VALUE_MASK = ~FLAG_MASK;
 
 template <typename KeyT>
 __device__ __forceinline__ uint32_t digit_of(KeyT k, int shift, int bits)
