@@ -84,13 +84,13 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_fwd_kernel(BlendArgs
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, Dd = 0.f, Aa = 0.f;
     uint32_t last = 0;
 
-    // software pipeline: the id / support box of chunk c+1 are loaded while chunk c is blended
-    uint32_t id_c = 0;
+    // software pipeline, two deep: while chunk c is blended the support boxes of chunk c+1 and the ids of chunk c+2
+    // are in flight (the id -> record address dependency never sits on the critical path)
+    uint32_t id_c = 0, id_n = 0;
     float4 g0_c = make_float4(0.f, 0.f, -1.f, -1.f);
-    if (lane < n_total) {
-        id_c = __ldg(plist + lane);
-        g0_c = __ldg(recs4 + 3 * (size_t)id_c);
-    }
+    if (lane < n_total) id_c = __ldg(plist + lane);
+    if (32 + lane < n_total) id_n = __ldg(plist + 32 + lane);
+    if (lane < n_total) g0_c = __ldg(recs4 + 3 * (size_t)id_c);
     for (int base = 0; base < n_total; base += 32) {
         if (__all_sync(FULL, T == 0.0f)) break;
         const bool hit = box_hits_patch(g0_c, fx0, fy0);
@@ -101,12 +101,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_fwd_kernel(BlendArgs
             g2 = __ldg(recs4 + 3 * (size_t)id_c + 2);
         }
         const float4 g0_h = g0_c;
-        const int e_n = base + 32 + lane;
+        id_c = id_n;
         g0_c = make_float4(0.f, 0.f, -1.f, -1.f);
-        if (e_n < n_total) {
-            id_c = __ldg(plist + e_n);
-            g0_c = __ldg(recs4 + 3 * (size_t)id_c);
-        }
+        if (base + 32 + lane < n_total) g0_c = __ldg(recs4 + 3 * (size_t)id_c);
+        if (base + 64 + lane < n_total) id_n = __ldg(plist + base + 64 + lane);
         if (b == 0u) continue;
         if (hit) {
             const int slot = __popc(b & lt);
@@ -256,12 +254,11 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
     float rg = 0.f, last_cg = 0.f, last_alpha = 0.f;
 
     // back to front: chunk [hi-32, hi), lane l <-> list position hi-1-l; the next chunk's loads are in flight
-    uint32_t id_c = 0;
+    uint32_t id_c = 0, id_n = 0;
     float4 g0_c = make_float4(0.f, 0.f, -1.f, -1.f);
-    if (wmax - 1 - lane >= 0) {
-        id_c = __ldg(plist + (wmax - 1 - lane));
-        g0_c = __ldg(recs4 + 3 * (size_t)id_c);
-    }
+    if (wmax - 1 - lane >= 0) id_c = __ldg(plist + (wmax - 1 - lane));
+    if (wmax - 33 - lane >= 0) id_n = __ldg(plist + (wmax - 33 - lane));
+    if (wmax - 1 - lane >= 0) g0_c = __ldg(recs4 + 3 * (size_t)id_c);
     for (int hi = wmax; hi > 0; hi -= 32) {
         const bool hit = box_hits_patch(g0_c, fx0, fy0);
         const uint32_t b = __ballot_sync(FULL, hit);
@@ -272,12 +269,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
         }
         const float4 g0_h = g0_c;
         const uint32_t id_h = id_c;
-        const int p_n = hi - 32 - 1 - lane;
+        id_c = id_n;
         g0_c = make_float4(0.f, 0.f, -1.f, -1.f);
-        if (p_n >= 0) {
-            id_c = __ldg(plist + p_n);
-            g0_c = __ldg(recs4 + 3 * (size_t)id_c);
-        }
+        if (hi - 33 - lane >= 0) g0_c = __ldg(recs4 + 3 * (size_t)id_c);
+        if (hi - 65 - lane >= 0) id_n = __ldg(plist + (hi - 65 - lane));
         if (b == 0u) continue;
         if (hit) {
             const int s = __popc(b & lt);
