@@ -13,8 +13,8 @@
 //   * Tile lists are exactly the reference's (tile/sort indices bit-identical); culling only skips pairs whose
 //     alpha is provably < 1/255, so images are unchanged.  Forward arithmetic follows the pinned order of
 //     common.cuh: images are bit-identical to the CPU oracle.
-//   * Backward: per-pixel terms are expressed as ten sums per Gaussian -- six sums of q = G*dL/dalpha
-//     (q, two mean-gradient forms, q dx^2, q dx dy, q dy^2) and four colour/depth weights -- reduced over the
+//   * Backward: per-pixel terms are expressed as ten sums per Gaussian -- six moments of q = G*dL/dalpha
+//     (1, dx, dy, dx^2, dx*dy, dy^2) and four colour/depth weights -- reduced over the
 //     32 lanes with a 12-shuffle multi-value butterfly (not 10 x 5 shuffles), then ten lanes each issue one
 //     red.global.add.f32 into the Gaussian's 48-byte ScreenGrad record.  Upstream: ~10 atomics per PIXEL.
 #include "common.cuh"
@@ -276,8 +276,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
         if (b == 0u) continue;
         if (hit) {
             const int s = __popc(b & lt);
-            // the support box has done its job: its two slots now carry -A and -C (= 2A', 2C') for the mean-gradient sums
-            sl.rec[3 * s] = make_float4(g0_h.x, g0_h.y, -g1.x, -g1.z);
+            sl.rec[3 * s] = g0_h;
             sl.rec[3 * s + 1] = make_float4(fmul(-0.5f, g1.x), -g1.y, fmul(-0.5f, g1.z), g1.w);
             sl.rec[3 * s + 2] = g2;
             sl.pos[s] = (uint32_t)(hi - 1 - lane);
@@ -309,12 +308,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
                 const float dL_dalpha = fmaf(T, cg - rg, -(Kbg * inv));
                 q = G * dL_dalpha;
             }
-            // Mx = -sum q (A dx + B dy), My = -sum q (C dy + B dx): formed per pixel (not from the moments sum q dx,
-            // sum q dy) so that the A.Sx + B.Sy cancellation of elongated Gaussians is not amplified by rounding.
+            // six moments of q over the patch: 1, dx, dy, dx^2, dx*dy, dy^2 (the conic / mean combination is linear
+            // and happens once per Gaussian in B2)
             const float qx = q * dx, qy = q * dy;
-            const float mx = q * fmaf(q1.y, dy, g0.z * dx);
-            const float my = q * fmaf(q1.y, dx, g0.w * dy);
-            const float e = butterfly10(q, mx, my, qx * dx, qx * dy, qy * dy, w * gC0, w * gC1, w * gC2, w * gD, lane);
+            const float e = butterfly10(q, qx, qy, qx * dx, qx * dy, qy * dy, w * gC0, w * gC1, w * gC2, w * gD, lane);
             if (slot >= 0) atomicAdd(sg_slot + 12 * (size_t)sl.id[i], e);
         }
         __syncwarp();
@@ -327,8 +324,8 @@ void launch_blend_bwd(const BlendBwdArgs &a, cudaStream_t st)
     blend_bwd_kernel<<<grid, 32 * WARPS_PER_CTA, 0, st>>>(a);
 }
 
-// ScreenGrad holds sums of q = G*dL/dalpha here: S0 = sum q, Mx = -sum q(A dx + B dy), My = -sum q(C dy + B dx),
-// Sxx, Sxy, Syy = sum q dx^2, q dx dy, q dy^2; then colour(3) and depth weights.
+// ScreenGrad holds moments of q = G*dL/dalpha here: S0, Sx, Sy, Sxx, Sxy, Syy = sum q*{1, dx, dy, dx^2, dx*dy, dy^2};
+// then colour(3) and depth weights.
 int blend_sgrad_is_moments() { return 1; }
 
 __global__ void test_exp_kernel(const float *x, float *y, int64_t n)

@@ -30,7 +30,7 @@ struct PreBwdArgs {
     const uint8_t *clamped;
     const ScreenGrad *sgrad; // [V*P]
     const GeomRec *recs;     // [V*P] forward records (conic, opacity) -- used when sgrad holds moments
-    int moments;             // 1: sgrad = (S0,Mx,My,Sxx,Sxy,Syy,cr,cg,cb,cd); 0: classic (dx,dy,dA,dBh,dC,dO,dr,dg,db,dd)
+    int moments;             // 1: sgrad = (S0,Sx,Sy,Sxx,Sxy,Syy,cr,cg,cb,cd); 0: classic (dx,dy,dA,dBh,dC,dO,dr,dg,db,dd)
     float *dL_dmeans3D, *dL_dmeans2D, *dL_dsh, *dL_dcolors, *dL_dopacity, *dL_dscales, *dL_drots, *dL_dcov3D;
 };
 

@@ -339,10 +339,10 @@ __global__ void __launch_bounds__(128, PBWD_MIN_BLOCKS) preprocess_bwd_kernel(Pr
         if (a.moments) {
             // moments of q = G*dL/dalpha over the Gaussian's pixels -> screen-space gradients (A.5)
             const float4 r1 = reinterpret_cast<const float4 *>(a.recs + vp)[1]; // conic A,B,C and opacity
-            const float S0 = g0.x, Mx = g0.y, My = g0.z, Sxx = g0.w, Sxy = g1.x, Syy = g1.y;
+            const float S0 = g0.x, Sx = g0.y, Sy = g0.z, Sxx = g0.w, Sxy = g1.x, Syy = g1.y;
             gO = S0;
-            gdx = r1.w * Mx * (0.5f * (float)a.W);
-            gdy = r1.w * My * (0.5f * (float)a.H);
+            gdx = -r1.w * (r1.x * Sx + r1.y * Sy) * (0.5f * (float)a.W);
+            gdy = -r1.w * (r1.z * Sy + r1.y * Sx) * (0.5f * (float)a.H);
             dA = -0.5f * r1.w * Sxx; dBh = -0.5f * r1.w * Sxy; dC = -0.5f * r1.w * Syy;
         } else {
             gdx = g0.x; gdy = g0.y; dA = g0.z; dBh = g0.w; dC = g1.x; gO = g1.y;
