@@ -314,6 +314,54 @@ int b200gs_pack_frames_u8(const float *color, uint8_t *out, int32_t image_height
     return B200GS_OK;
 }
 
+int b200gs_densify_stats(int32_t P, int32_t n_views, const float *dL_dmeans2D, const int32_t *radii, float *xyz_gradient_accum,
+                         float *denom, float *max_radii2D, void *stream)
+{
+    if (P < 0 || n_views < 1 || !dL_dmeans2D || !radii || !xyz_gradient_accum || !denom || !max_radii2D) return B200GS_E_ARGS;
+    if (P == 0) return B200GS_OK;
+    launch_densify_stats(P, n_views, dL_dmeans2D, radii, xyz_gradient_accum, denom, max_radii2D, (cudaStream_t)stream);
+    g_launches += 1;
+    CK(cudaGetLastError(), "densify_stats launch");
+    return B200GS_OK;
+}
+
+size_t b200gs_densify_scratch_bytes(int32_t P) { return densify_scratch_bytes(P < 0 ? 0 : P); }
+
+int b200gs_densify_plan(int32_t P, const b200gs_densify_cfg *cfg, const float *xyz_gradient_accum, const float *denom,
+                        const float *opacity_raw, const float *scaling_raw, int32_t *plan, int32_t *counts, void *scratch,
+                        size_t scratch_bytes, void *stream)
+{
+    if (P < 1 || !cfg || !opacity_raw || !scaling_raw || !plan || !counts || !scratch) return B200GS_E_ARGS;
+    if (cfg->mode != 0 && cfg->mode != 1) return B200GS_E_ARGS;
+    if (cfg->mode == 0 && (!xyz_gradient_accum || !denom || cfg->n_split < 1)) return B200GS_E_ARGS;
+    if (cfg->n_split > 16 || (int64_t)P * (1 + (cfg->mode == 0 ? 1 + cfg->n_split : 0)) > 0x7fffffffLL) return B200GS_E_RANGE;
+    if (scratch_bytes < densify_scratch_bytes(P)) return B200GS_E_BUFFER;
+    DensifyCfg c;
+    c.mode = cfg->mode; c.n_split = cfg->mode == 0 ? cfg->n_split : 0; c.use_screen = cfg->use_screen;
+    c.max_grad = cfg->max_grad; c.min_opacity = cfg->min_opacity; c.dense_thresh = cfg->percent_dense_x_extent;
+    c.max_screen_size = cfg->max_screen_size; c.big_ws_thresh = cfg->big_ws_thresh;
+    launch_densify_plan(c, P, xyz_gradient_accum, denom, opacity_raw, scaling_raw, plan, counts, (char *)scratch, (cudaStream_t)stream);
+    g_launches += 3;
+    CK(cudaGetLastError(), "densify_plan launch");
+    return B200GS_OK;
+}
+
+int b200gs_densify_move(int32_t role, int32_t P, int32_t row_floats, const int32_t *plan, const int32_t *counts_host, int32_t n_split,
+                        const float *src, float *dst, const float *rotation_raw, const float *scaling_raw, const float *noise, void *stream)
+{
+    if (P < 1 || row_floats < 1 || role < 0 || role > 3 || !plan || !counts_host || !src || n_split < 0) return B200GS_E_ARGS;
+    const int S_sel = counts_host[2], S_kept = counts_host[3];
+    const int64_t P_new = (int64_t)counts_host[0] + counts_host[1] + (int64_t)n_split * S_kept;
+    if (counts_host[0] < 0 || counts_host[1] < 0 || S_sel < 0 || S_kept < 0 || S_kept > S_sel || counts_host[4] != P_new) return B200GS_E_ARGS;
+    if (P_new > 0 && !dst) return B200GS_E_ARGS;
+    if (role == B200GS_ROLE_XYZ && (row_floats != 3 || (S_kept > 0 && (!rotation_raw || !scaling_raw || !noise)))) return B200GS_E_ARGS;
+    if (P_new == 0) return B200GS_OK;
+    launch_densify_move(role, P, row_floats, plan, src, dst, n_split, S_sel, S_kept, rotation_raw, scaling_raw, noise, (cudaStream_t)stream);
+    g_launches += 1;
+    CK(cudaGetLastError(), "densify_move launch");
+    return B200GS_OK;
+}
+
 int b200gs_test_sort_pairs(uint32_t *keys_a, uint32_t *keys_b, uint32_t *vals_a, uint32_t *vals_b, int64_t n, int32_t nbits,
                            void *scratch, size_t scratch_bytes, int32_t *result_in_b, void *stream)
 {

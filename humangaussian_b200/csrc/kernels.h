@@ -93,3 +93,21 @@ void launch_pack_u8(const float *color, uint8_t *out, int H, int W, int n_frames
 // 3-nearest-neighbour mean squared distance (knn.cu)
 size_t knn_scratch_bytes(int P);
 int launch_knn3(int P, const float *pts, float *mean_d2, char *scratch, size_t scratch_bytes, cudaStream_t st, int *n_launches);
+
+// densify / prune (densify.cu)
+struct DensifyCfg {
+    int mode;            // 0 = densify_and_prune, 1 = prune_only
+    int n_split;         // children per split parent (reference: 2)
+    int use_screen;      // reference's `if max_screen_size:` branch
+    float max_grad, min_opacity;
+    float dense_thresh;  // percent_dense * extent
+    float max_screen_size;
+    float big_ws_thresh; // 0.1 * extent (mode 0) or size_thresh (mode 1)
+};
+size_t densify_scratch_bytes(int P);
+void launch_densify_stats(int P, int V, const float *grads, const int32_t *radii, float *accum, float *denom, float *max_radii2D,
+                          cudaStream_t st);
+void launch_densify_plan(const DensifyCfg &c, int P, const float *accum, const float *denom, const float *opacity, const float *scaling,
+                         int *plan, int *counts, char *scratch, cudaStream_t st);
+void launch_densify_move(int role, int P, int rf, const int *plan, const float *src, float *dst, int n_split, int S_sel, int S_kept,
+                         const float *rotation, const float *scaling, const float *noise, cudaStream_t st);

@@ -137,6 +137,49 @@ int b200gs_pack_frames_u8(const float *color, uint8_t *out, int32_t image_height
 size_t b200gs_knn_scratch_bytes(int32_t P);
 int b200gs_dist2_knn3(int32_t P, const float *points, float *mean_dist2, void *scratch, size_t scratch_bytes, void *stream);
 
+/* ---- densification / pruning on the device (reference gaussiansplatting/scene/gaussian_model.py:268-437, driven from
+ * threestudio/systems/GaussianDreamer.py:378-408) ----------------------------------------------------------------------
+ * Parameters are the RAW (pre-activation) optimiser tensors, one array per group as the reference holds them.
+ *
+ * b200gs_densify_stats: one optimiser step's bookkeeping for a V-view batch (GaussianDreamer.py:385-391 +
+ *   add_densification_stats, gaussian_model.py:433-437): g = sum_v dL_dmeans2D[v] ; r = max_v radii[v] ; where r > 0:
+ *   max_radii2D = max(max_radii2D, r), xyz_gradient_accum += |g.xy|, denom += 1.
+ *     dL_dmeans2D [V,P,3] (what b200gs_backward wrote), radii [V,P] int32; accum, denom, max_radii2D [P] (in/out). */
+int b200gs_densify_stats(int32_t P, int32_t n_views, const float *dL_dmeans2D, const int32_t *radii,
+                         float *xyz_gradient_accum, float *denom, float *max_radii2D, void *stream);
+
+typedef struct b200gs_densify_cfg {
+    int32_t mode;            /* 0 = densify_and_prune (gaussian_model.py:402-415), 1 = prune_only (:423-430) */
+    int32_t n_split;         /* children per split Gaussian; the reference uses N = 2 */
+    int32_t use_screen;      /* mode 0: the reference's `if max_screen_size:` (None / 0 -> 0) */
+    float max_grad;          /* mode 0 */
+    float min_opacity;
+    float percent_dense_x_extent; /* mode 0: clone at or below, split above */
+    float max_screen_size;   /* mode 0 with use_screen (compared with the statistics AFTER their reset, as the reference does) */
+    float big_ws_thresh;     /* mode 0 with use_screen: 0.1 * extent;  mode 1: size_thresh */
+} b200gs_densify_cfg;
+
+/* Plans the surgery.  plan [4,P] int32 (device): rows = destination of the surviving original, of its clone, of its first
+ * split child (child c lands S_kept*c rows further), and the parent's row in the noise block; -1 = none.
+ * counts [5] int32 (device): n_keep, n_clone, S_sel (split parents), S_kept (split parents whose children survive),
+ * P_new = n_keep + n_clone + n_split*S_kept.  Output row order is the reference's: surviving unsplit originals, clones,
+ * children copy 0, children copy 1.  scratch: b200gs_densify_scratch_bytes(P). */
+size_t b200gs_densify_scratch_bytes(int32_t P);
+int b200gs_densify_plan(int32_t P, const b200gs_densify_cfg *cfg, const float *xyz_gradient_accum, const float *denom,
+                        const float *opacity_raw, const float *scaling_raw, int32_t *plan, int32_t *counts,
+                        void *scratch, size_t scratch_bytes, void *stream);
+
+/* Moves one [P,row_floats] array to its planned [P_new,row_floats] place.  role: */
+enum { B200GS_ROLE_COPY = 0,    /* new rows repeat the parent row (f_dc, f_rest, opacity, rotation; statistics in mode 1) */
+       B200GS_ROLE_XYZ = 1,     /* children: R(rotation) (noise * exp(scaling)) + xyz  (gaussian_model.py:369-373) */
+       B200GS_ROLE_SCALING = 2, /* children: log(exp(scaling) / (0.8 n_split))          (gaussian_model.py:374) */
+       B200GS_ROLE_MOMENT = 3 };/* Adam exp_avg / exp_avg_sq: new rows are zero         (gaussian_model.py:317-341) */
+/*   counts_host [5]: the plan's counts, read back by the caller (it needs P_new to allocate dst anyway);
+ *   rotation_raw [P,4], scaling_raw [P,3], noise [n_split*S_sel,3] standard-normal draws: only read for B200GS_ROLE_XYZ. */
+int b200gs_densify_move(int32_t role, int32_t P, int32_t row_floats, const int32_t *plan, const int32_t *counts_host,
+                        int32_t n_split, const float *src, float *dst, const float *rotation_raw, const float *scaling_raw,
+                        const float *noise, void *stream);
+
 /* ---- introspection of the state buffers, for parity tests (tile/sort indices must match bit-for-bit) ------- */
 typedef struct b200gs_state_view {
     const void *geom_records;     /* [V*P] x 48 B: px,py,hx,hy | conicA,conicB,conicC,opacity | r,g,b,depth */
