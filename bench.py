@@ -60,32 +60,51 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
-    def start(self):
+    def start(self, wait_s=5.0):
+        """Launch nvidia-smi and wait for its first row, so that sampling is already running when the (sub-second)
+        timed region begins; rows are stamped on arrival and only those inside [begin(), end()] are reported."""
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            t = time.perf_counter()
+            while not self.rows and time.perf_counter() - t < wait_s:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc:
+            time.sleep(0.06)  # let the last in-window row arrive
             self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        t0 = self.t0 if self.t0 is not None else -1e30
+        t1 = (self.t1 if self.t1 is not None else 1e30) + 0.06
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 9]
+        window = "timed region"
+        if not rows:  # region shorter than one sampling period: fall back to the rows nearest to it, and say so
+            rows = [r for _, r in self.rows[-3:] if len(r) >= 9]
+            window = "nearest samples (timed region shorter than the sampling period)"
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
+        for r in rows:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------- CPU reference
@@ -305,8 +324,14 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(2):
+        step()  # keep the GPU busy right up to the timed region (nvidia-smi start-up took a moment)
+    torch.cuda.synchronize()
+    R.profile_read()
     l0 = R.launch_count()
+    sampler.begin()
     ms_total = timed(args.steps)
+    sampler.end()
     launches = R.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     stages = R.profile_read()
@@ -327,16 +352,17 @@ def run_b200(args):
     bytes_stage = None
     roof = None
     if D is not None:
+        Vc = 1 if args.per_view else V  # views per launch set: the per-view pattern makes one call (one launch set) per view
         bytes_stage = {
             # F1 reads the P Gaussians ONCE per batch (view loop inside the thread) and writes per-view state
-            "preprocess_fwd": P * G_in + V * P * 8 + n_vis * G_mid,
+            "preprocess_fwd": P * G_in + Vc * P * 8 + n_vis * G_mid,
             # depth pre-sort of V*P (8 B key + 4 B index, one read + one write = single-pass lower bound) + scan
-            "scan": V * P * (24 + 8),
+            "scan": Vc * P * (24 + 8),
             # emit (8 B) + stable tile sort (single-pass bound: 8 B read + 8 B write) + ranges (4 B read + tiles*8)
-            "binning": D * 8 + D * 16 + D * 4 + V * (pix // 256) * 8,
-            "blend_fwd": D * (4 + G_mid) + V * pix * 28,
-            "blend_bwd": V * pix * 28 + D * (4 + G_mid) + n_vis * G_mid,
-            "preprocess_bwd": n_vis * G_mid + P * G_in + P * (G_in + 12) + V * P * 12,
+            "binning": D * 8 + D * 16 + D * 4 + Vc * (pix // 256) * 8,
+            "blend_fwd": D * (4 + G_mid) + Vc * pix * 28,
+            "blend_bwd": Vc * pix * 28 + D * (4 + G_mid) + n_vis * G_mid,
+            "preprocess_bwd": n_vis * G_mid + P * G_in + P * (G_in + 12) + Vc * P * 12,
         }
         table = {}
         for k, (ms, calls) in stages.items():
@@ -350,7 +376,7 @@ def run_b200(args):
         traffic, traffic_src = None, None
         try:  # DRAM bytes per launch of the dominant kernel, from the committed ncu capture (per view x views of this launch)
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = int(tj[dom]["dram_bytes_per_view"] * V)
+            traffic = int(tj[dom]["dram_bytes_per_view"] * Vc)
             traffic_src = tj[dom]["capture"]
         except Exception:
             pass
