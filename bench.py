@@ -356,8 +356,8 @@ def run_b200(args):
         bytes_stage = {
             # F1 reads the P Gaussians ONCE per batch (view loop inside the thread) and writes per-view state
             "preprocess_fwd": P * G_in + Vc * P * 8 + n_vis * G_mid,
-            # depth pre-sort of V*P (8 B key + 4 B index, one read + one write = single-pass lower bound) + scan
-            "scan": Vc * P * (24 + 8),
+            # depth pre-sort of V*P (4 B key + 4 B index, one read + one write = single-pass lower bound) + scan
+            "scan": Vc * P * (16 + 8),
             # emit (8 B) + stable tile sort (single-pass bound: 8 B read + 8 B write) + ranges (4 B read + tiles*8)
             "binning": D * 8 + D * 16 + D * 4 + Vc * (pix // 256) * 8,
             "blend_fwd": D * (4 + G_mid) + Vc * pix * 28,

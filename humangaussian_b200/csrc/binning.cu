@@ -3,7 +3,8 @@
 // Upstream sorts D = sum(tiles_touched) 64-bit (tile|depth) keys: ~7 radix passes over every (Gaussian, tile)
 // instance.  The order it defines -- inside each tile ascending depth, ties by ascending Gaussian index -- is
 // reproduced here with far less traffic:
-//   1. sort the V*P Gaussians once by (view, depth bits)   [stable LSD radix, 8-bit digits; V*P is 4-5x smaller than D]
+//   1. sort the V*P Gaussians once by depth bits (all views mixed: step 4's key carries the view)
+//                                                          [stable LSD radix, 4 passes of 8-bit digits on 4-byte keys; V*P is 4-5x smaller than D]
 //   2. inclusive scan of tiles_touched IN THAT ORDER        [single-pass decoupled look-back] -> D and emission offsets
 //   3. emit instances in depth order: key = view*tiles + tile (32 bit), value = record index
 //   4. STABLE sort by the tile key only                     [9-bit digits: 2 passes for 12..18 bits, 8-byte pairs]
@@ -25,7 +26,7 @@ static int bits_for(uint64_t n)
 }
 
 // sort configuration
-constexpr int D_BITS = 8, D_IPT = 8, D_TILE = THREADS * D_IPT;    // depth sort: u64 keys
+constexpr int D_BITS = 8, D_IPT = 12, D_TILE = THREADS * D_IPT;   // depth sort: u32 keys (the depth bits)
 constexpr int T_BITS = 9, T_IPT = 12, T_TILE = THREADS * T_IPT;   // tile sort: u32 keys
 constexpr int MAXP = 5;
 constexpr int SCAN_TILE = THREADS * SCAN_IPT;
@@ -47,8 +48,8 @@ BinLayout binning_layout(int64_t capacity, int ntiles_total, int64_t n_vp)
     L.vals_in = o; o += gs_align(cap * 4);
     L.vals_out = o; o += gs_align(cap * 4);
     L.ranges = o; o += gs_align((size_t)ntiles_total * 8);
-    L.dkeys_in = o; o += gs_align(nvp * 8);
-    L.dkeys_out = o; o += gs_align(nvp * 8);
+    L.dkeys_in = o; o += gs_align(nvp * 4);
+    L.dkeys_out = o; o += gs_align(nvp * 4);
     L.order_in = o; o += gs_align(nvp * 4);
     L.order = o; o += gs_align(nvp * 4);
     L.tile_order = o; o += gs_align((size_t)ntiles_total * 4);
@@ -100,11 +101,10 @@ static int radix_sort_pairs(KeyT *ka, KeyT *kb, uint32_t *va, uint32_t *vb, int6
 int launch_depth_order(const uint32_t *tiles_touched, uint32_t *offsets_sorted, int64_t n_vp, int V, char *bin_base,
                        const BinLayout &L, const uint32_t **order_sorted, cudaStream_t st, int *n_launches)
 {
-    uint64_t *ks = nullptr;
-    uint32_t *vs = nullptr;
-    if (radix_sort_pairs<uint64_t, D_BITS, D_IPT>((uint64_t *)(bin_base + L.dkeys_in), (uint64_t *)(bin_base + L.dkeys_out),
+    uint32_t *ks = nullptr, *vs = nullptr;
+    if (radix_sort_pairs<uint32_t, D_BITS, D_IPT>((uint32_t *)(bin_base + L.dkeys_in), (uint32_t *)(bin_base + L.dkeys_out),
                                                   (uint32_t *)(bin_base + L.order_in), (uint32_t *)(bin_base + L.order), n_vp,
-                                                  32 + bits_for((uint64_t)V), bin_base + L.temp, L.temp_bytes, &ks, &vs, st, n_launches))
+                                                  32, bin_base + L.temp, L.temp_bytes, &ks, &vs, st, n_launches))
         return -1;
     *order_sorted = vs;
     const size_t nblocks = (size_t)((n_vp + SCAN_TILE - 1) / SCAN_TILE);

@@ -15,7 +15,7 @@ struct PreArgs {
     uint32_t *tiles_touched; // [V*P]
     uint2 *rects;            // [V*P]
     uint8_t *clamped;        // [V*P]
-    uint64_t *dkeys;         // [V*P] (view << 32) | depth bits   (input of the depth pre-sort)
+    uint32_t *dkeys;         // [V*P] depth bits (input of the depth pre-sort; the view rides in the tile key)
     uint32_t *order_in;      // [V*P] = vp
 };
 
@@ -66,7 +66,7 @@ void launch_mark_visible(int P, const float *pos, const float *V, uint8_t *prese
 // binning: depth pre-sort of the V*P Gaussians, scan in depth order, tile-key emission, stable tile sort, ranges
 struct BinLayout {
     size_t keys_in, keys_out, vals_in, vals_out, ranges; // per-instance tile keys (u32) / record indices (u32), tile ranges
-    size_t dkeys_in, dkeys_out, order_in, order;         // per-Gaussian (view|depth) keys (u64) and the depth order (u32)
+    size_t dkeys_in, dkeys_out, order_in, order;         // per-Gaussian depth keys (u32) and the depth order (u32)
     size_t tile_order, tile_order_cnt;                   // launch order of the tiles (longest list first) + 32 bucket counters
     size_t temp, total;
     size_t temp_bytes;

@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256, PFWD_MIN_BLOCKS) preprocess_fwd_kernel(Pr
         } while (0);
 
         a.radii[vp] = radius;
-        a.dkeys[vp] = ((uint64_t)v << 32) | (uint64_t)__float_as_uint(rec.depth); // culled: depth 0 sorts first, emits nothing
+        a.dkeys[vp] = __float_as_uint(rec.depth); // culled: depth 0 sorts first, emits nothing
         a.order_in[vp] = (uint32_t)vp;
         a.tiles_touched[vp] = tiles;
         a.rects[vp] = rect_pack;

@@ -188,7 +188,7 @@ typedef struct b200gs_state_view {
     const uint8_t *clamped;       /* [V*P] bit c set = channel c clamped at 0 */
     const uint32_t *sorted_tile_keys; /* [num_rendered] view*tiles + tile of each sorted instance; the reference's 64-bit key
                                          of instance j is (sorted_tile_keys[j] << 32) | bits(depth of record point_list[j]) */
-    const uint32_t *depth_order;  /* [V*P] record indices sorted by (view, depth bits, index) */
+    const uint32_t *depth_order;  /* [V*P] record indices (view*P + i) sorted by (depth bits, record index), all views mixed */
     const uint32_t *point_list;   /* [num_rendered] Gaussian index of each sorted instance */
     const uint32_t *ranges;       /* [V*tiles][2] */
     const float *final_T;         /* [V,H,W] */

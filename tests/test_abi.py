@@ -40,7 +40,7 @@ def test_size_queries_are_sane(lib):
     assert lib.b200gs_geom_bytes(1000, 4) >= 4 * 1000 * 65
     assert lib.b200gs_image_bytes(64, 64, 2) >= 2 * 64 * 64 * 8
     a, b = lib.b200gs_binning_bytes(1000, 64, 64, 100, 1), lib.b200gs_binning_bytes(100000, 64, 64, 100, 1)
-    assert b > a >= 1000 * 16 + 100 * 24  # 16 B per instance + 24 B per Gaussian (depth pre-sort)
+    assert b > a >= 1000 * 16 + 100 * 16  # 16 B per instance + 16 B per Gaussian (depth pre-sort: 4 B keys + indices, ping-pong)
     assert lib.b200gs_backward_scratch_bytes(1000, 2) >= 2000 * 48
 
 
