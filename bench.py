@@ -279,9 +279,9 @@ def run_b200(args):
                                       camposs=v_cp[i:i + 1], tanfovx=tanx[i:i + 1], tanfovy=tany[i:i + 1], image_height=HW,
                                       image_width=HW, bg=bg, sh_degree=deg, shs=sh, scales=sc, rotations=rot) for i in range(V)]
             c, r, d, a = (torch.cat([o[k] for o in outs], 0) for k in range(4))
-        else:
-            c, r, d, a = R.rasterize_views(means3D=xyz, opacities=op, viewmatrices=v_vm, projmatrices=v_pm, camposs=v_cp, tanfovx=tanx,
-                                           tanfovy=tany, image_height=HW, image_width=HW, bg=bg, sh_degree=deg, shs=sh, scales=sc, rotations=rot)
+        else:  # the batched entry over the packed buffer: B3 writes flat.grad (the all-reduce payload) in place
+            c, r, d, a = R.rasterize_views_packed(f, P, K, viewmatrices=v_vm, projmatrices=v_pm, camposs=v_cp, tanfovx=tanx, tanfovy=tany,
+                                                  image_height=HW, image_width=HW, bg=bg, sh_degree=deg)
         if e2e:
             loss = (c * gw[0]).sum() + (d * gw[1]).sum() + (a * gw[2]).sum()
             loss.backward()

@@ -237,18 +237,21 @@ def _forward_impl(means3D, shs, colors_precomp, opacities, scales, rotations, co
 
 
 def _backward_impl(st: _Ctx, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, viewmatrix,
-                   projmatrix, campos, g_color, g_depth, g_alpha):
+                   projmatrix, campos, g_color, g_depth, g_alpha, out=None):
+    """`out` (optional): dict of preallocated contiguous fp32 gradient buffers by name (means3D, sh, opacity, scales,
+    rotations) -- the packed entry points them into one flat buffer so that B3 writes the all-reduce payload in place."""
     L = load_library()
     dev = means3D.device
     P, V, M = st.P, st.V, st.M
     f = dict(dtype=torch.float32, device=dev)
-    d_means3D = torch.empty(means3D.shape, **f)  # [P,3], or [V,P,3] for per-view positions
+    out = out or {}
+    d_means3D = out.get("means3D") if "means3D" in out else torch.empty(means3D.shape, **f)  # [P,3], or [V,P,3] per-view
     d_means2D = torch.empty(V, P, 3, **f)
-    d_op = torch.empty(P, 1, **f)
-    d_sh = torch.empty(P, M, 3, **f) if shs is not None else None
+    d_op = out.get("opacity") if "opacity" in out else torch.empty(P, 1, **f)
+    d_sh = (out.get("sh") if "sh" in out else torch.empty(P, M, 3, **f)) if shs is not None else None
     d_col = torch.empty(P, 3, **f) if colors_precomp is not None else None
-    d_sc = torch.empty(P, 3, **f) if scales is not None else None
-    d_rot = torch.empty(P, 4, **f) if rotations is not None else None
+    d_sc = (out.get("scales") if "scales" in out else torch.empty(P, 3, **f)) if scales is not None else None
+    d_rot = (out.get("rotations") if "rotations" in out else torch.empty(P, 4, **f)) if rotations is not None else None
     d_cov = torch.empty(P, 6, **f) if cov3D_precomp is not None else None
     if P == 0:
         return d_means3D, d_means2D, d_sh, d_col, d_op, d_sc, d_rot, d_cov
@@ -378,6 +381,70 @@ def rasterize_views(*, means3D, opacities, viewmatrices, projmatrices, camposs, 
     cams = (bg, viewmatrices, projmatrices, camposs, list(tanfovx), list(tanfovy), int(image_height), int(image_width),
             int(sh_degree), float(scale_modifier), False, False)
     return _RasterizeViews.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, cams, False)
+
+
+# ---- packed entry: one flat SoA parameter buffer in, one flat gradient buffer out ---------------------------------
+PACKED_FIELDS = ("xyz", "scales", "rotations", "opacities", "shs")  # == dist.FIELDS order
+
+
+def packed_numel(P: int, sh_coeffs: int) -> int:
+    return P * (11 + 3 * sh_coeffs)
+
+
+def _split_packed(flat: torch.Tensor, P: int, M: int):
+    """contiguous views [P,3] [P,3] [P,4] [P,1] [P,M,3] into the flat buffer (no copies)"""
+    o, outs = 0, []
+    for n, shape in ((3 * P, (P, 3)), (3 * P, (P, 3)), (4 * P, (P, 4)), (P, (P, 1)), (3 * M * P, (P, M, 3))):
+        outs.append(flat.narrow(0, o, n).view(shape))
+        o += n
+    return outs
+
+
+class _RasterizePacked(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, packed, means2D, P, M, cams):
+        bg, viewmatrix, projmatrix, campos, tanx, tany, H, W, deg, mod = cams
+        dev = packed.device
+        xyz, sc, rot, op, sh = _split_packed(packed.detach(), P, M)
+        camt = [_f32c(t, dev) for t in (bg, viewmatrix, projmatrix, campos)]
+        color, radii, depth, alpha, st = _forward_impl(xyz, sh, None, op, sc, rot, None, *camt, tanx, tany, H, W, deg, mod)
+        ctx.st, ctx.saved, ctx.P, ctx.M = st, [packed.detach()] + camt, P, M
+        ctx.mark_non_differentiable(radii)
+        return color, radii, depth, alpha
+
+    @staticmethod
+    def backward(ctx, g_color, g_radii, g_depth, g_alpha):
+        packed, bg, viewmatrix, projmatrix, campos = ctx.saved
+        P, M, dev = ctx.P, ctx.M, packed.device
+        xyz, sc, rot, op, sh = _split_packed(packed, P, M)
+        d_packed = torch.empty_like(packed)
+        d_xyz, d_sc, d_rot, d_op, d_sh = _split_packed(d_packed, P, M)
+        g = [None if t is None else _f32c(t, dev) for t in (g_color, g_depth, g_alpha)]
+        _, d_means2D, *_ = _backward_impl(ctx.st, xyz, sh, None, op, sc, rot, None, bg, viewmatrix, projmatrix, campos, *g,
+                                          out=dict(means3D=d_xyz, sh=d_sh, opacity=d_op, scales=d_sc, rotations=d_rot))
+        ctx.st = ctx.saved = None
+        return d_packed, d_means2D, None, None, None
+
+
+def rasterize_views_packed(packed: torch.Tensor, P: int, sh_coeffs: int, *, viewmatrices, projmatrices, camposs, tanfovx, tanfovy,
+                           image_height, image_width, bg, sh_degree=0, means2D=None, scale_modifier=1.0):
+    """`rasterize_views` over ONE flat fp32 buffer [xyz 3P | scales 3P | rotations 4P | opacities P | shs 3*K*P]
+    (post-activation values; the layout `dist.pack` produces, broadcast once per parameter version).  The backward
+    kernels write the parameter gradients straight into one buffer of the same layout, which becomes `packed.grad`
+    as is: no per-tensor gradient accumulation, and on several GPUs that buffer is the all-reduce payload in place.
+    V <= MAX_VIEWS.  Returns color [V,3,H,W], radii [V,P], depth [V,1,H,W], alpha [V,1,H,W]."""
+    if packed.dim() != 1 or packed.numel() != packed_numel(P, sh_coeffs) or packed.dtype != torch.float32 or not packed.is_contiguous():
+        raise ValueError(f"b200gs: packed buffer must be contiguous fp32 with {packed_numel(P, sh_coeffs)} elements")
+    if packed.device.type != "cuda":
+        raise RuntimeError("b200gs: tensors must live on a CUDA device (there is no CPU path)")
+    V = viewmatrices.shape[0]
+    if V > MAX_VIEWS:
+        raise ValueError(f"b200gs: at most {MAX_VIEWS} views per packed call")
+    if means2D is None:
+        means2D = torch.zeros(V, P, 3, dtype=torch.float32, device=packed.device)
+    cams = (bg, viewmatrices, projmatrices, camposs, list(tanfovx), list(tanfovy), int(image_height), int(image_width),
+            int(sh_degree), float(scale_modifier))
+    return _RasterizePacked.apply(packed, means2D, int(P), int(sh_coeffs), cams)
 
 
 # ---- test / debugging access to the forward state (tile and sort indices) -----------------------------------

@@ -166,3 +166,40 @@ def test_only_some_inputs_require_grad():
                                                   scales=g("scales"), rotations=g("rotations"))
     c.sum().backward()
     assert xyz.grad is not None and float(xyz.grad.abs().max()) > 0
+
+
+def test_packed_entry_is_bitwise_the_batched_entry():
+    """rasterize_views_packed: same kernels over views of one flat buffer; the gradient arrives as ONE flat buffer that
+    the backward kernels wrote in place (no per-tensor accumulation) and equals the per-tensor gradients bit for bit."""
+    from humangaussian_b200.cameras import sample_orbit_cameras
+    from humangaussian_b200.dist import pack, unpack
+    from humangaussian_b200.rasterizer import rasterize_views, rasterize_views_packed
+    from humangaussian_b200.renderer import stack_cameras
+    P, K, H, W, V = 1500, 4, 48, 64, 5
+    inp, _, _ = small_scene(P=P, deg=1, seed=4, H=H, W=W)
+    cams = sample_orbit_cameras(V, H, W, seed=8, device=DEV)
+    vm, pm, cp, tanx, tany = stack_cameras(cams, DEV)
+    g = lambda k: torch.tensor(inp[k], device=DEV)
+    t = dict(xyz=g("means3D"), scaling=g("scales"), rotation=g("rotations"), opacity=g("opacities").reshape(P, 1), features=g("shs"))
+    assert t["features"].shape == (P, K, 3)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in t.items()}
+    m2d = torch.zeros(V, P, 3, device=DEV, requires_grad=True)
+    cam = dict(viewmatrices=vm, projmatrices=pm, camposs=cp, tanfovx=tanx, tanfovy=tany, image_height=H, image_width=W, bg=g("bg"), sh_degree=1)
+    c, r, d, a = rasterize_views(means3D=leaves["xyz"], opacities=leaves["opacity"], shs=leaves["features"], scales=leaves["scaling"],
+                                 rotations=leaves["rotation"], means2D=m2d, **cam)
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    gw = [torch.randn(x.shape, device=DEV, generator=gen) for x in (c, d, a)]
+    torch.autograd.backward([c, d, a], gw)
+    flat = pack(t).requires_grad_(True)
+    m2d_p = torch.zeros(V, P, 3, device=DEV, requires_grad=True)
+    c2, r2, d2, a2 = rasterize_views_packed(flat, P, K, means2D=m2d_p, **cam)
+    assert torch.equal(c, c2) and torch.equal(r, r2) and torch.equal(d, d2) and torch.equal(a, a2)
+    torch.autograd.backward([c2, d2, a2], gw)
+    # same kernels, same inputs; the blend backward sums with float atomics, so two runs agree to rounding, not bitwise
+    ref = pack({k: v.grad for k, v in leaves.items()})
+    assert flat.grad.shape == ref.shape
+    for got, want in zip(unpack(flat.grad, P, K).values(), unpack(ref, P, K).values()):
+        assert float((got - want).abs().max()) <= 1e-6 + 1e-5 * float(want.abs().max())
+    assert float((m2d.grad - m2d_p.grad).abs().max()) <= 1e-6 + 1e-5 * float(m2d.grad.abs().max()) and float(m2d.grad.abs().max()) > 0
+    with pytest.raises(ValueError):
+        rasterize_views_packed(flat[:-1], P, K, **cam)
