@@ -200,7 +200,7 @@ def run_reference(args):
                              "sample": "each step = 1 view (of the 64-view batch) fwd+bwd by oracle/gs_oracle.c with all host threads"},
             "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t_all}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, n):
@@ -228,7 +228,8 @@ def run_b200(args):
     torch.cuda.set_device(dev)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("B200GS_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        if "B200GS_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["B200GS_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev)
     R.load_library()
     P, V, HW, deg = args.gaussians, args.views, args.res, args.sh_degree
@@ -412,7 +413,7 @@ def run_b200(args):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
                 "views_per_step_per_gpu": V, "instances_per_step": D, "visible_per_step": n_vis,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        emit(line)
         if args.stage_json and roof:
             os.makedirs(os.path.dirname(os.path.abspath(args.stage_json)), exist_ok=True)
             json.dump({"ms_per_step": ms_step, "views_per_s": value, "stages": roof["stages"], "clocks": clocks}, open(args.stage_json, "w"), indent=1)
@@ -420,8 +421,26 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout; everything else written to fd 1 during the run
+    (NCCL's version banner, library chatter) was re-routed to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     args = parse()
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)  # C-level writers to stdout (e.g. "NCCL version ...") must not pollute the one-line contract
     if args.impl == "classic":
         os.environ["B200GS_LIB"] = os.path.join(ROOT, "baseline", "libb200gs_classic.so")
         args.no_cpu_baseline = True
