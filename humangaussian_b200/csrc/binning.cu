@@ -116,42 +116,81 @@ int launch_depth_order(const uint32_t *tiles_touched, uint32_t *offsets_sorted, 
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-// one thread per Gaussian IN DEPTH ORDER: writes its tile keys at the offsets the scan assigned
+// Instance emission, warp-cooperative.  A warp owns 32 consecutive Gaussians IN DEPTH ORDER; their instances form one
+// contiguous run [start of lane 0, end of lane 31) of the output, so lane j writes output element base+j (fully coalesced
+// 128-byte stores) after finding its owner Gaussian with a 5-step shuffle binary search over the 32 run starts.
+// (A thread-per-Gaussian loop writes 4-byte words 18 bytes apart on average: 1.1 TB/s, measured.)
 __global__ void __launch_bounds__(256) emit_tiles_kernel(const uint32_t *__restrict__ order, const uint2 *__restrict__ rects,
                                                           const uint32_t *__restrict__ offsets_sorted, int P, int64_t n_vp,
                                                           int grid_x, int ntiles, uint32_t *__restrict__ keys,
                                                           uint32_t *__restrict__ vals)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_vp) return;
-    const uint32_t vp = order[k];
-    const uint2 r = rects[vp];
-    const int x0 = r.x & 0xffff, y0 = r.x >> 16, x1 = r.y & 0xffff, y1 = r.y >> 16;
-    if (x1 <= x0 || y1 <= y0) return;
-    uint32_t off = (k == 0) ? 0u : offsets_sorted[k - 1];
-    const uint32_t tile_base = (uint32_t)(vp / (uint32_t)P) * (uint32_t)ntiles;
-    for (int y = y0; y < y1; y++)
-        for (int x = x0; x < x1; x++) {
-            keys[off] = tile_base + (uint32_t)(y * grid_x + x);
-            vals[off] = vp;
-            off++;
+    const int lane = threadIdx.x & 31;
+    uint32_t vp = 0, x0 = 0, y0 = 0, w = 1, cnt = 0, end = 0;
+    if (k < n_vp) {
+        vp = order[k];
+        const uint2 r = rects[vp];
+        const uint32_t rx0 = r.x & 0xffff, ry0 = r.x >> 16, rx1 = r.y & 0xffff, ry1 = r.y >> 16;
+        end = offsets_sorted[k];
+        if (rx1 > rx0 && ry1 > ry0) { x0 = rx0; y0 = ry0; w = rx1 - rx0; cnt = w * (ry1 - ry0); }
+    }
+    // lanes past n_vp: empty runs starting where the last valid lane ends
+    const int64_t k_last = n_vp - 1;
+    const int last_valid = (int)min((int64_t)31, k_last - (k - lane));
+    end = __shfl_sync(0xffffffffu, end, min(lane, last_valid));
+    if (k >= n_vp) cnt = 0;
+    const uint32_t start = end - cnt;
+    const uint32_t tile_base = (vp / (uint32_t)P) * (uint32_t)ntiles + y0 * (uint32_t)grid_x + x0;
+    const uint32_t warp_start = __shfl_sync(0xffffffffu, start, 0), warp_end = __shfl_sync(0xffffffffu, end, 31);
+    for (uint32_t base = warp_start; base < warp_end; base += 32) {
+        const uint32_t j = base + lane;
+        int lo = 0; // largest lane whose run starts at or before j (empty runs share their successor's start, so the
+                    // last lane with that start is the one that owns j)
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const uint32_t s = __shfl_sync(0xffffffffu, start, (lo + step) & 31);
+            if (lo + step < 32 && s <= j) lo += step;
         }
-}
-
-__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t *__restrict__ keys, int64_t D, uint2 *__restrict__ ranges)
-{
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= D) return;
-    const uint32_t t = keys[j];
-    if (j == 0) ranges[t].x = 0;
-    else {
-        const uint32_t tp = keys[j - 1];
-        if (tp != t) {
-            ranges[tp].y = (uint32_t)j;
-            ranges[t].x = (uint32_t)j;
+        const uint32_t o_start = __shfl_sync(0xffffffffu, start, lo);
+        const uint32_t o_w = __shfl_sync(0xffffffffu, w, lo);
+        const uint32_t o_base = __shfl_sync(0xffffffffu, tile_base, lo);
+        const uint32_t o_vp = __shfl_sync(0xffffffffu, vp, lo);
+        if (j < warp_end) {
+            const uint32_t local = j - o_start;
+            const uint32_t dy = local / o_w, dx = local - dy * o_w;
+            keys[j] = o_base + dy * (uint32_t)grid_x + dx;
+            vals[j] = o_vp;
         }
     }
-    if (j == D - 1) ranges[t].y = (uint32_t)D;
+}
+
+// tile boundaries of the sorted keys: four keys per thread (one 128-bit load + the neighbour before)
+__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t *__restrict__ keys, int64_t D, uint2 *__restrict__ ranges)
+{
+    const int64_t j0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (j0 >= D) return;
+    uint32_t t[4];
+    if (j0 + 3 < D) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(keys + j0);
+        t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w;
+    } else {
+        for (int i = 0; i < 4; i++) t[i] = (j0 + i < D) ? keys[j0 + i] : 0u;
+    }
+    uint32_t prev = (j0 == 0) ? 0u : keys[j0 - 1];
+    if (j0 == 0) ranges[t[0]].x = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int64_t j = j0 + i;
+        if (j < D) {
+            if (j > 0 && prev != t[i]) {
+                ranges[prev].y = (uint32_t)j;
+                ranges[t[i]].x = (uint32_t)j;
+            }
+            if (j == D - 1) ranges[t[i]].y = (uint32_t)D;
+            prev = t[i];
+        }
+    }
 }
 
 // ---- launch order of the tiles: longest list first (LPT).  One view is otherwise bounded by its heaviest tiles being
@@ -224,7 +263,7 @@ int launch_binning(const uint32_t *order_sorted, const uint2 *rects, const uint3
     uint32_t *ks = nullptr, *vs = nullptr;
     if (radix_sort_pairs<uint32_t, T_BITS, T_IPT>(k0, k1, v0, v1, D, nbits, bin_base + L.temp, L.temp_bytes, &ks, &vs, st, n_launches)) return -2;
     if (ks != keys_out || vs != vals_out) return -4;
-    tile_ranges_kernel<<<(unsigned)((D + 255) / 256), 256, 0, st>>>(keys_out, D, ranges);
+    tile_ranges_kernel<<<(unsigned)((D + 1023) / 1024), 256, 0, st>>>(keys_out, D, ranges);
     cudaMemsetAsync(tcnt, 0, 64 * 4, st);
     tile_bucket_count_kernel<<<(nt_all + 255) / 256, 256, 0, st>>>(ranges, nt_all, tcnt);
     tile_bucket_scatter_kernel<<<(nt_all + 255) / 256, 256, 0, st>>>(ranges, nt_all, tcnt, tile_order);
