@@ -25,7 +25,7 @@
 #define WARPS_PER_CTA 2 // independent patches per CTA (1, 2, 4 or 8); swept on B200: 2 is best by ~2 %
 #endif
 #ifndef BWD_MIN_BLOCKS
-#define BWD_MIN_BLOCKS 16 // caps the backward kernel at 64 registers (32 warps/SM)
+#define BWD_MIN_BLOCKS 16 // caps the backward kernel at 64 registers (32 warps/SM); 18 / 20 blocks (55 / 48 regs) measured slower
 #endif
 #define CTAS_PER_TILE (8 / WARPS_PER_CTA)
 
