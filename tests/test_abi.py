@@ -70,3 +70,46 @@ def test_cpu_tensors_are_rejected():
     z = torch.zeros
     with pytest.raises(RuntimeError, match="CUDA device"):
         GaussianRasterizer(s)(means3D=z(4, 3), means2D=z(4, 3), shs=z(4, 1, 3), opacities=z(4, 1), scales=z(4, 3), rotations=z(4, 4))
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of every struct that crosses the ABI, as gcc sees include/b200gs.h, equal the ctypes mirrors."""
+    import ctypes as C
+    import subprocess
+    from humangaussian_b200 import densify, rasterizer
+    src = tmp_path / "layout.c"
+    fields = {"b200gs_params": [f[0] for f in rasterizer._Params._fields_],
+              "b200gs_densify_cfg": [f[0] for f in densify._Cfg._fields_],
+              "b200gs_state_view": [f[0] for f in rasterizer._StateView._fields_]}
+    body = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200gs.h"', 'int main(void){']
+    for s, fs in fields.items():
+        body.append(f'printf("{s} %zu\\n", sizeof({s}));')
+        for f in fs:
+            body.append(f'printf("{s}.{f} %zu\\n", offsetof({s}, {f}));')
+    body.append("return 0;}")
+    src.write_text("\n".join(body))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    mirrors = {"b200gs_params": rasterizer._Params, "b200gs_densify_cfg": densify._Cfg, "b200gs_state_view": rasterizer._StateView}
+    for s, cls in mirrors.items():
+        assert int(got[s]) == C.sizeof(cls), s
+        for f in fields[s]:
+            assert int(got[f"{s}.{f}"]) == getattr(cls, f).offset, f"{s}.{f}"
+
+
+def test_packed_layout_is_dist_pack_layout():
+    """rasterize_views_packed reads the buffer dist.pack writes: same field order, same views (pure torch, CPU)."""
+    import torch
+    from humangaussian_b200 import dist as D
+    from humangaussian_b200 import rasterizer as R
+    P, K = 7, 4
+    g = torch.Generator().manual_seed(0)
+    t = {k: torch.randn(*shape, generator=g) for k, shape in D.field_shapes(P, K).items()}
+    flat = D.pack(t)
+    assert flat.numel() == R.packed_numel(P, K)
+    for got, want in zip(R._split_packed(flat, P, K), (t[k] for k in D.FIELDS)):
+        assert torch.equal(got, want) and got.data_ptr() >= flat.data_ptr()
+    with __import__("pytest").raises((RuntimeError, ValueError)):
+        R.rasterize_views_packed(flat, P, K, viewmatrices=torch.eye(4)[None], projmatrices=torch.eye(4)[None], camposs=torch.zeros(1, 3),
+                                 tanfovx=[1.0], tanfovy=[1.0], image_height=8, image_width=8, bg=torch.zeros(3))  # CPU tensors: no fallback
