@@ -236,13 +236,14 @@ def run_b200(args):
     K = (deg + 1) ** 2
 
     # ---- the scene: one flat SoA parameter buffer [xyz | scale | rot | opacity | sh], broadcast once from rank 0
-    sizes = [3 * P, 3 * P, 4 * P, P, 3 * K * P]
-    flat = torch.empty(sum(sizes), device=dev)
-    host_flat = torch.empty(sum(sizes), pin_memory=True)
+    fields, n_flat = R.packed_layout(P, K)  # every field 16-byte aligned (dist.pack's layout)
+    flat = torch.zeros(n_flat, device=dev)
+    host_flat = torch.zeros(n_flat, pin_memory=True)
     if rank == 0:
         p = synthetic_body(P, sh_degree=deg, seed=0)
         with torch.no_grad():
-            host_flat.copy_(torch.cat([t.reshape(-1) for t in (p.get_xyz, p.get_scaling, p.get_rotation, p.get_opacity, p.get_features)]))
+            for (o, n, _), t in zip(fields, (p.get_xyz, p.get_scaling, p.get_rotation, p.get_opacity, p.get_features)):
+                host_flat.narrow(0, o, n).copy_(t.reshape(-1))
         flat.copy_(host_flat, non_blocking=True)
     if world > 1:
         dist.broadcast(flat, 0)  # 4*59*P bytes over NVLink, once per parameter version
@@ -250,12 +251,7 @@ def run_b200(args):
     flat.requires_grad_(True)
 
     def views_of(f):
-        o = 0
-        outs = []
-        for n, shape in zip(sizes, [(P, 3), (P, 3), (P, 4), (P, 1), (P, K, 3)]):
-            outs.append(f.narrow(0, o, n).view(shape))
-            o += n
-        return outs
+        return [f.narrow(0, o, n).view(shape) for o, n, shape in fields]
 
     cams = sample_orbit_cameras(V, HW, HW, seed=1000 + rank, device=dev)
     vm, pm, cp, tanx, tany = stack_cameras(cams, dev)
@@ -297,7 +293,7 @@ def run_b200(args):
         stats["n_vis"] = r
         return r
 
-    host_grad = torch.empty(sum(sizes), pin_memory=True)
+    host_grad = torch.empty(n_flat, pin_memory=True)
 
     def timed(n_steps, e2e=False):
         if world > 1:

@@ -102,6 +102,7 @@ int b200gs_forward(const b200gs_params *prm, const float *means3D, const float *
     const ImageLayout IL(H, W, V);
     const BinLayout BL = binning_layout(instance_capacity, gx * gy * V, (int64_t)P * V);
     if (geom_bytes < GL.total || image_bytes < IL.total || binning_bytes < BL.total) return B200GS_E_BUFFER;
+    if ((((uintptr_t)geom_buf) | ((uintptr_t)binning_buf) | ((uintptr_t)image_buf)) & 15) return B200GS_E_BUFFER; // records are 128-bit accessed
     char *gb = (char *)geom_buf, *bb = (char *)binning_buf, *ib = (char *)image_buf;
     const size_t HW = (size_t)H * W;
     *num_rendered = 0;
@@ -113,6 +114,7 @@ int b200gs_forward(const b200gs_params *prm, const float *means3D, const float *
     } else {
         PreArgs a;
         a.P = P; a.deg = shs ? prm->sh_degree : 0; a.M = prm->sh_coeffs; a.H = H; a.W = W; a.grid_x = gx; a.grid_y = gy;
+        a.vec16 = ((((uintptr_t)rotations) | ((uintptr_t)shs)) & 15) == 0; // any 4-byte-aligned float pointer is accepted
         a.mod = prm->scale_modifier;
         a.means_view_stride = prm->means3D_per_view ? (size_t)3 * P : 0;
         a.means = means3D; a.shs = shs; a.colors_pre = colors_precomp; a.opac = opacities; a.scales = scales;
@@ -184,6 +186,7 @@ int b200gs_backward(const b200gs_params *prm, const float *means3D, const float 
     const ImageLayout IL(H, W, V);
     const BinLayout BL = binning_layout(instance_capacity, gx * gy * V, (int64_t)P * V);
     if (scratch_bytes < b200gs_backward_scratch_bytes(P, V)) return B200GS_E_BUFFER;
+    if ((((uintptr_t)geom_buf) | ((uintptr_t)binning_buf) | ((uintptr_t)image_buf) | ((uintptr_t)scratch)) & 15) return B200GS_E_BUFFER;
     const char *gb = (const char *)geom_buf, *bb = (const char *)binning_buf, *ib = (const char *)image_buf;
 
     CK(cudaMemsetAsync(scratch, 0, (size_t)P * V * sizeof(ScreenGrad), st), "memset scratch");
@@ -199,6 +202,7 @@ int b200gs_backward(const b200gs_params *prm, const float *means3D, const float 
 
     PreBwdArgs a;
     a.P = P; a.V = V; a.deg = shs ? prm->sh_degree : 0; a.M = prm->sh_coeffs; a.H = H; a.W = W; a.mod = prm->scale_modifier;
+    a.vec16 = (((uintptr_t)dL_drots) & 15) == 0;
     a.means_view_stride = prm->means3D_per_view ? (size_t)3 * P : 0;
     a.means = means3D; a.shs = shs; a.colors_pre = colors_precomp; a.scales = scales; a.rots = rotations; a.cov_pre = cov3D_precomp;
     a.view = viewmatrix; a.proj = projmatrix; a.campos = campos;

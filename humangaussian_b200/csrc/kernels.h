@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 struct PreArgs {
+    int vec16;               // rotations and shs are 16-byte aligned: 128-bit loads allowed
     int P, deg, M, H, W, grid_x, grid_y;
     size_t means_view_stride; // 0: means shared by all views; 3*P: per-view positions
     float mod;
@@ -20,6 +21,7 @@ struct PreArgs {
 };
 
 struct PreBwdArgs {
+    int vec16;               // dL_drots is 16-byte aligned: 128-bit store allowed
     int P, V, deg, M, H, W;
     size_t means_view_stride; // as PreArgs; when non-zero dL_dmeans3D is [V,P,3] (per view, not summed)
     float mod;

@@ -100,8 +100,14 @@ __global__ void __launch_bounds__(256, PFWD_MIN_BLOCKS) preprocess_fwd_kernel(Pr
     } else {
         const float s3[3] = {__ldg(a.scales + 3 * (size_t)i), __ldg(a.scales + 3 * (size_t)i + 1),
                              __ldg(a.scales + 3 * (size_t)i + 2)};
-        const float4 q4 = __ldg(reinterpret_cast<const float4 *>(a.rots) + i);
-        const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+        float q[4];
+        if (a.vec16) {
+            const float4 q4 = __ldg(reinterpret_cast<const float4 *>(a.rots) + i);
+            q[0] = q4.x; q[1] = q4.y; q[2] = q4.z; q[3] = q4.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) q[k] = __ldg(a.rots + 4 * (size_t)i + k);
+        }
         build_cov3d(s3, a.mod, q, c6);
     }
     float shc[3 * NB]; // SH coefficients [k][channel], or the precomputed colour
@@ -111,7 +117,7 @@ __global__ void __launch_bounds__(256, PFWD_MIN_BLOCKS) preprocess_fwd_kernel(Pr
         shc[2] = __ldg(a.colors_pre + 3 * (size_t)i + 2);
     } else {
         const float *sh = a.shs + (size_t)i * a.M * 3;
-        if ((3 * NB) % 4 == 0 && (a.M & 3) == 0) { // 16-byte aligned rows: 128-bit loads
+        if ((3 * NB) % 4 == 0 && (a.M & 3) == 0 && a.vec16) { // 16-byte aligned rows: 128-bit loads
             const float4 *sh4 = reinterpret_cast<const float4 *>(sh);
 #pragma unroll
             for (int k = 0; k < (3 * NB) / 4; k++) {
@@ -507,7 +513,11 @@ __global__ void __launch_bounds__(128, PBWD_MIN_BLOCKS) preprocess_bwd_kernel(Pr
         dq.y = 2.f * y * (dR[0][1] + dR[1][0]) + 2.f * z * (dR[0][2] + dR[2][0]) + 2.f * r * (dR[2][1] - dR[1][2]) - 4.f * x * (dR[1][1] + dR[2][2]);
         dq.z = 2.f * x * (dR[0][1] + dR[1][0]) + 2.f * r * (dR[0][2] - dR[2][0]) + 2.f * z * (dR[1][2] + dR[2][1]) - 4.f * y * (dR[0][0] + dR[2][2]);
         dq.w = 2.f * r * (dR[1][0] - dR[0][1]) + 2.f * x * (dR[0][2] + dR[2][0]) + 2.f * y * (dR[1][2] + dR[2][1]) - 4.f * z * (dR[0][0] + dR[1][1]);
-        reinterpret_cast<float4 *>(a.dL_drots)[i] = dq;
+        if (a.vec16) reinterpret_cast<float4 *>(a.dL_drots)[i] = dq;
+        else {
+            float *o = a.dL_drots + 4 * (size_t)i;
+            o[0] = dq.x; o[1] = dq.y; o[2] = dq.z; o[3] = dq.w;
+        }
     }
 }
 

@@ -2,7 +2,7 @@
 so views / animation frames shard across ranks and the rasteriser itself never communicates.
 
 One process per GPU (torchrun); `torch.distributed` backend "nccl" on GPUs, "gloo" in the CPU tests.
-  * pack / unpack       -- one flat SoA buffer [xyz | scale | rot | opacity | sh] = what is broadcast / all-reduced
+  * pack / unpack       -- one flat SoA buffer [xyz | scale | rot | opacity | sh] (fields 16-byte aligned) = what is broadcast / all-reduced
   * broadcast_scene     -- once per parameter version (4*(11+3K)*P bytes: 70.8 MB at P=300k, deg 3)
   * shard_views         -- SDS batch: round-robin (GaussianDreamer.py:244-248); animation: contiguous blocks (animation.py:1002-1013)
   * allreduce_gradients -- training only: one all-reduce of the packed gradient buffer; radii by MAX (GaussianDreamer.py:253-256)
@@ -22,23 +22,27 @@ def field_shapes(P: int, sh_coeffs: int):
     return {"xyz": (P, 3), "scaling": (P, 3), "rotation": (P, 4), "opacity": (P, 1), "features": (P, sh_coeffs, 3)}
 
 
+def _layout(P: int, sh_coeffs: int):
+    from .rasterizer import packed_layout  # one definition of the flat layout (16-byte aligned fields)
+    return packed_layout(P, sh_coeffs)
+
+
 def pack(tensors: dict) -> torch.Tensor:
-    return torch.cat([tensors[k].reshape(-1) for k in FIELDS])
+    P, K = tensors["xyz"].shape[0], tensors["features"].shape[1]
+    fields, total = _layout(P, K)
+    x = tensors["xyz"]
+    flat = torch.zeros(total, dtype=x.dtype, device=x.device)
+    for k, (o, n, _) in zip(FIELDS, fields):
+        flat.narrow(0, o, n).copy_(tensors[k].reshape(-1))
+    return flat
 
 
 def unpack(flat: torch.Tensor, P: int, sh_coeffs: int) -> dict:
     """Contiguous VIEWS into the flat buffer (no copies): gradients written through them land in flat.grad."""
-    need = P * (11 + 3 * sh_coeffs)
+    fields, need = _layout(P, sh_coeffs)
     if flat.dim() != 1 or flat.numel() != need:
         raise ValueError(f"flat buffer has {flat.numel()} elements, layout needs {need}")
-    out, o = {}, 0
-    for k, shape in field_shapes(P, sh_coeffs).items():
-        n = 1
-        for s in shape:
-            n *= s
-        out[k] = flat.narrow(0, o, n).view(shape)
-        o += n
-    return out
+    return {k: flat.narrow(0, o, n).view(shape) for k, (o, n, shape) in zip(FIELDS, fields)}
 
 
 def is_dist() -> bool:

@@ -387,17 +387,24 @@ def rasterize_views(*, means3D, opacities, viewmatrices, projmatrices, camposs, 
 PACKED_FIELDS = ("xyz", "scales", "rotations", "opacities", "shs")  # == dist.FIELDS order
 
 
+def packed_layout(P: int, sh_coeffs: int):
+    """[(offset, numel, shape)] of xyz, scales, rotations, opacities, shs in the flat buffer, and its total length (floats).
+    Every field starts on a 16-byte boundary (offsets rounded up to 4 floats), so the kernels' 128-bit loads/stores of
+    rotations and SH rows stay legal for any P; for P % 4 == 0 the fields are simply back to back."""
+    out, o = [], 0
+    for n, shape in ((3 * P, (P, 3)), (3 * P, (P, 3)), (4 * P, (P, 4)), (P, (P, 1)), (3 * sh_coeffs * P, (P, sh_coeffs, 3))):
+        out.append((o, n, shape))
+        o = (o + n + 3) & ~3
+    return out, o
+
+
 def packed_numel(P: int, sh_coeffs: int) -> int:
-    return P * (11 + 3 * sh_coeffs)
+    return packed_layout(P, sh_coeffs)[1]
 
 
 def _split_packed(flat: torch.Tensor, P: int, M: int):
     """contiguous views [P,3] [P,3] [P,4] [P,1] [P,M,3] into the flat buffer (no copies)"""
-    o, outs = 0, []
-    for n, shape in ((3 * P, (P, 3)), (3 * P, (P, 3)), (4 * P, (P, 4)), (P, (P, 1)), (3 * M * P, (P, M, 3))):
-        outs.append(flat.narrow(0, o, n).view(shape))
-        o += n
-    return outs
+    return [flat.narrow(0, o, n).view(shape) for o, n, shape in packed_layout(P, M)[0]]
 
 
 class _RasterizePacked(torch.autograd.Function):
@@ -417,7 +424,7 @@ class _RasterizePacked(torch.autograd.Function):
         packed, bg, viewmatrix, projmatrix, campos = ctx.saved
         P, M, dev = ctx.P, ctx.M, packed.device
         xyz, sc, rot, op, sh = _split_packed(packed, P, M)
-        d_packed = torch.empty_like(packed)
+        d_packed = torch.empty_like(packed) if P % 4 == 0 else torch.zeros_like(packed)  # alignment padding carries zero gradient
         d_xyz, d_sc, d_rot, d_op, d_sh = _split_packed(d_packed, P, M)
         g = [None if t is None else _f32c(t, dev) for t in (g_color, g_depth, g_alpha)]
         _, d_means2D, *_ = _backward_impl(ctx.st, xyz, sh, None, op, sc, rot, None, bg, viewmatrix, projmatrix, campos, *g,
@@ -428,8 +435,9 @@ class _RasterizePacked(torch.autograd.Function):
 
 def rasterize_views_packed(packed: torch.Tensor, P: int, sh_coeffs: int, *, viewmatrices, projmatrices, camposs, tanfovx, tanfovy,
                            image_height, image_width, bg, sh_degree=0, means2D=None, scale_modifier=1.0):
-    """`rasterize_views` over ONE flat fp32 buffer [xyz 3P | scales 3P | rotations 4P | opacities P | shs 3*K*P]
-    (post-activation values; the layout `dist.pack` produces, broadcast once per parameter version).  The backward
+    """`rasterize_views` over ONE flat fp32 buffer [xyz 3P | scales 3P | rotations 4P | opacities P | shs 3*K*P], each
+    field starting on a 16-byte boundary (`packed_layout`; post-activation values; what `dist.pack` produces, broadcast
+    once per parameter version).  The backward
     kernels write the parameter gradients straight into one buffer of the same layout, which becomes `packed.grad`
     as is: no per-tensor gradient accumulation, and on several GPUs that buffer is the all-reduce payload in place.
     V <= MAX_VIEWS.  Returns color [V,3,H,W], radii [V,P], depth [V,1,H,W], alpha [V,1,H,W]."""

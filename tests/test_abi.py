@@ -113,3 +113,21 @@ def test_packed_layout_is_dist_pack_layout():
     with __import__("pytest").raises((RuntimeError, ValueError)):
         R.rasterize_views_packed(flat, P, K, viewmatrices=torch.eye(4)[None], projmatrices=torch.eye(4)[None], camposs=torch.zeros(1, 3),
                                  tanfovx=[1.0], tanfovy=[1.0], image_height=8, image_width=8, bg=torch.zeros(3))  # CPU tensors: no fallback
+
+
+def test_packed_layout_fields_are_16_byte_aligned_for_any_P():
+    import torch
+    from humangaussian_b200 import dist as D
+    from humangaussian_b200 import rasterizer as R
+    for P in (1, 2, 3, 5, 531327, 300000):
+        for K in (1, 4, 16):
+            fields, total = R.packed_layout(P, K)
+            assert all(o % 4 == 0 for o, _, _ in fields) and total % 4 == 0
+            assert total >= P * (11 + 3 * K) and total - P * (11 + 3 * K) < 5 * 4
+            if P % 4 == 0:
+                assert total == P * (11 + 3 * K)  # back to back: nothing changes for the bench configuration
+    P, K = 5, 4
+    g = torch.Generator().manual_seed(1)
+    t = {k: torch.randn(*shape, generator=g) for k, shape in D.field_shapes(P, K).items()}
+    back = D.unpack(D.pack(t), P, K)
+    assert all(torch.equal(back[k], t[k]) for k in t)

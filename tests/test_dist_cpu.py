@@ -19,7 +19,7 @@ def _worker(rank, world, port, n_views, P, K, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        n = P * (11 + 3 * K)
+        n = D._layout(P, K)[1]
         flat = torch.arange(n, dtype=torch.float32) * 1e-3 if rank == 0 else torch.zeros(n)
         D.broadcast_scene(flat, 0)
         f = D.unpack(flat, P, K)
@@ -44,7 +44,7 @@ def test_two_rank_view_sharding(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, n_views, P, K, str(tmp_path)), nprocs=world, join=True)
     r = [torch.load(tmp_path / f"r{i}.pt") for i in range(world)]
-    ref_flat = torch.arange(P * (11 + 3 * K), dtype=torch.float32) * 1e-3
+    ref_flat = torch.arange(D._layout(P, K)[1], dtype=torch.float32) * 1e-3
     want = sum(_fake_grad(ref_flat, v) for v in range(n_views))
     for i in range(world):
         assert torch.equal(r[i]["flat"], ref_flat)                      # broadcast reached every rank

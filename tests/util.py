@@ -59,7 +59,7 @@ def close_rows(a, b, atol=1e-5, rtol=1e-4):
     return bool((err <= lim).all()), float((err / lim).max()) if err.size else 0.0
 
 
-def grads_agree(a, b, atol=1e-5, rtol=1e-4, min_elementwise=0.999):
+def grads_agree(a, b, atol=1e-5, rtol=1e-4, min_elementwise=0.999, min_rows=1.0, row_cap=1.0):
     """The gradient parity criterion of the GPU tests.
 
     A per-Gaussian gradient is a float32 sum over hundreds of pixels with heavy cancellation (the mean/scale derivatives
@@ -78,5 +78,9 @@ def grads_agree(a, b, atol=1e-5, rtol=1e-4, min_elementwise=0.999):
     row_lim = atol + rtol * np.abs(b2).max(axis=1, keepdims=True)
     row_worst = float((err / row_lim).max())
     el_ok = float((err <= atol + rtol * np.abs(b2)).mean())
-    ok = row_worst <= 1.0 and el_ok >= min_elementwise
-    return ok, f"row-wise worst {row_worst:.2f}x of tolerance, elementwise pass rate {100 * el_ok:.4f}%"
+    rows_ok = float(((err / row_lim).max(axis=1) <= 1.0).mean())
+    # parity tests: every row inside the tolerance (min_rows = 1, row_cap = 1).  Property tests that compare two
+    # NON-DETERMINISTIC float32 evaluations at full size may allow a 1e-4 fraction of ill-conditioned rows up to row_cap.
+    ok = rows_ok >= min_rows and row_worst <= max(row_cap, 1.0) and el_ok >= min_elementwise
+    return ok, (f"row-wise worst {row_worst:.2f}x of tolerance, rows inside {100 * rows_ok:.4f}%, "
+                f"elementwise pass rate {100 * el_ok:.4f}%")
