@@ -195,7 +195,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "fwd+bwd views/sec @1024^2, ~300k Gaussians", "value": value, "unit": "views/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(dts) / len(dts),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, 1),
+            "config": workload_config(args, args.gpus),  # the GPU arm's config (rank 0 alone runs this arm on the host CPU)
             "cpu_baseline": {"value": value, "unit": "views/s", "cores": cores, "kind": "port",
                              "sample": "each step = 1 view (of the 64-view batch) fwd+bwd by oracle/gs_oracle.c with all host threads"},
             "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
