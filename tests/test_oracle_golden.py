@@ -173,3 +173,25 @@ def test_camera_batch_equals_per_camera():
         assert torch.allclose(cb.camera_center[i], c.camera_center, atol=1e-6)
         assert abs(cb.tanfovx[i] - math.tan(c.FoVx / 2)) < 1e-12 and abs(cb.tanfovy[i] - math.tan(c.FoVy / 2)) < 1e-12
     assert len(sample_orbit_cameras(3, 64, 64, seed=1)) == 3
+
+
+def test_oracle_reproduces_its_frozen_vectors():
+    """The oracle defines the numerical contract the kernels are tested against; its outputs on a stored scene are frozen
+    (tests/golden/make_oracle_frozen.py).  Forward state must reproduce bit for bit, gradients to 1e-6 relative."""
+    from oracle.gs_oracle import Oracle
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_frozen.npz"))
+    inp = {k[3:]: z[k] for k in z.files if k.startswith("in_")}
+    for k in ("sh_degree", "image_height", "image_width"):
+        inp[k] = int(inp[k])
+    for k in ("tanfovx", "tanfovy", "scale_modifier"):
+        inp[k] = float(inp[k])
+    o = Oracle(threads=3)
+    color, radii, depth, alpha = o.forward(**inp)
+    st = o.state()
+    for name, got in (("color", color), ("radii", radii), ("depth", depth), ("alpha", alpha), ("point_list", st["point_list"]),
+                      ("ranges", st["ranges"]), ("keys", st["keys"]), ("n_contrib", st["n_contrib"]), ("final_T", st["final_T"])):
+        assert np.array_equal(got, z[name]), name
+    grads = o.backward(z["g_color"], z["g_depth"], z["g_alpha"])
+    for k, v in grads.items():
+        if v is not None:
+            np.testing.assert_allclose(v, z["grad_" + k], rtol=1e-6, atol=1e-9, err_msg=k)
