@@ -244,13 +244,8 @@ int b200gs_describe_state(const b200gs_params *prm, const void *geom_buf, const 
     out->offsets = (const uint32_t *)(gb + GL.offsets);
     out->clamped = (const uint8_t *)(gb + GL.clamped);
     out->sorted_tile_keys = (const uint32_t *)(bb + BL.keys_out);
-    // the depth sort takes ceil((32 + bits(V)) / 8) ping-pong passes starting from order_in
-    {
-        int vb = 0;
-        while ((1 << vb) < V) vb++;
-        const int npass = (32 + vb + 7) / 8;
-        out->depth_order = (const uint32_t *)(bb + ((npass & 1) ? BL.order : BL.order_in));
-    }
+    // the depth sort takes 32 / 8 = 4 ping-pong passes starting from order_in: an even count ends where it began
+    out->depth_order = (const uint32_t *)(bb + BL.order_in);
     out->point_list = (const uint32_t *)(bb + BL.vals_out);
     out->ranges = (const uint32_t *)(bb + BL.ranges);
     out->final_T = (const float *)(ib + IL.final_T);

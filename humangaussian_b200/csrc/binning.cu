@@ -113,7 +113,7 @@ int launch_depth_order(const uint32_t *tiles_touched, uint32_t *offsets_sorted, 
     scan_tiles_kernel<<<(unsigned)nblocks, THREADS, 0, st>>>(vs, tiles_touched, offsets_sorted, n_vp, (volatile uint64_t *)(scr + 256),
                                                             (uint32_t *)scr);
     *n_launches += 1;
-    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
 }
 
 // Instance emission, warp-cooperative.  A warp owns 32 consecutive Gaussians IN DEPTH ORDER; their instances form one
