@@ -35,6 +35,42 @@ __device__ __forceinline__ bool box_hits_patch(const float4 g0, float x0, float 
     return (g0.z >= 0.0f) && (g0.x + g0.z >= x0) && (g0.x - g0.z <= x0 + 7.0f) && (g0.y + g0.w >= y0) && (g0.y - g0.w <= y0 + 3.0f);
 }
 
+// Exact version of the same question for the hits of the box test: does the ellipse {Q <= tau}, Q(u,v) = (A u^2 + C v^2)/2 + B u v
+// around the Gaussian's centre, tau = ln(255 o) (+ the conditioning-aware margin of preprocess.cu), reach the rectangle?
+// The minimum of the convex Q over the rectangle [u0,u1] x [v0,v1] (u = X - px) is 0 if the centre is inside; otherwise it
+// lies on the edge facing the centre in x or in y (KKT: on a far edge dQ/dn has the wrong sign because det > 0), where it
+// is a clamped 1-D parabola minimum.  Continuous minimum <= minimum over the pixel lattice: conservative.
+__device__ __forceinline__ bool ellipse_hits_patch(const float4 g0, const float4 g1, float x0, float y0)
+{
+    const float A = g1.x, B = g1.y, C = g1.z;
+    const float k255 = 255.0f * g1.w;
+    const float AC = A * C, dt = AC - B * B;
+    const float aniso = __fdividef(AC, dt); // = 1/(1-rho^2) >= 1
+    if (!(aniso < 1.0e4f)) return true;     // too ill-conditioned to bound safely (NaN included): never cull
+    const float tau = __logf(k255) * (1.0f + 1.0e-5f * aniso) + 0.03f;
+    const float u0 = x0 - g0.x, u1 = u0 + 7.0f, v0 = y0 - g0.y, v1 = v0 + 3.0f;
+    const float ue = fminf(fmaxf(0.0f, u0), u1), ve = fminf(fmaxf(0.0f, v0), v1);
+    const float vs = fminf(fmaxf(__fdividef(-B * ue, C), v0), v1);
+    const float us = fminf(fmaxf(__fdividef(-B * ve, A), u0), u1);
+    const float Q1 = ue * (0.5f * A * ue + B * vs) + 0.5f * C * vs * vs;
+    const float Q2 = us * (0.5f * A * us + B * ve) + 0.5f * C * ve * ve;
+    return fminf(Q1, Q2) <= tau;
+}
+
+#ifdef BLEND_COUNTERS
+// instrumentation build only (tests/gpu_r2_probe.py): visit statistics of the patch walk
+__device__ unsigned long long g_blend_cnt[16];
+#define CNT_ADD(i, v) do { if (lane == 0) atomicAdd(&g_blend_cnt[i], (unsigned long long)(v)); } while (0)
+extern "C" int b200gs_debug_counters(unsigned long long *out, int reset)
+{
+    cudaMemcpyFromSymbol(out, g_blend_cnt, sizeof(g_blend_cnt));
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_blend_cnt, z, sizeof(z)); }
+    return 0;
+}
+#else
+#define CNT_ADD(i, v) do { } while (0)
+#endif
+
 // power with the conic pre-scaled at staging time (A' = -A/2, B' = -B, C' = -C/2: exact operations, so the
 // result is bit-identical to gs_power(A,B,C,dx,dy))
 __device__ __forceinline__ float power_prescaled(float Ap, float Bp, float Cp, float dx, float dy)
@@ -105,6 +141,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_fwd_kernel(BlendArgs
         g0_c = make_float4(0.f, 0.f, -1.f, -1.f);
         if (base + 32 + lane < n_total) g0_c = __ldg(recs4 + 3 * (size_t)id_c);
         if (base + 64 + lane < n_total) id_n = __ldg(plist + base + 64 + lane);
+#ifdef BLEND_COUNTERS
+        CNT_ADD(0, 1); CNT_ADD(1, min(32, n_total - base)); CNT_ADD(2, __popc(b));
+        CNT_ADD(3, __popc(__ballot_sync(FULL, hit && ellipse_hits_patch(g0_h, g1, fx0, fy0))));
+#endif
         if (b == 0u) continue;
         if (hit) {
             const int slot = __popc(b & lt);
@@ -119,6 +159,13 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_fwd_kernel(BlendArgs
             const float4 g0 = sl.rec[3 * i], q1 = sl.rec[3 * i + 1];
             const float dx = fsub(g0.x, fpx), dy = fsub(g0.y, fpy);
             const float power = power_prescaled(q1.x, q1.y, q1.z, dx, dy);
+#ifdef BLEND_COUNTERS
+            {
+                const bool el = !(power > 0.0f) && !(fminf(GS_ALPHA_MAX, fmul(q1.w, gs_exp(power))) < GS_ALPHA_MIN);
+                const uint32_t be = __ballot_sync(FULL, el), bc = __ballot_sync(FULL, el && T != 0.0f);
+                CNT_ADD(4, bc != 0u); CNT_ADD(5, __popc(bc)); CNT_ADD(6, be != 0u); CNT_ADD(7, bc != 0u && __popc(bc) < 8);
+            }
+#endif
             if (!(power > 0.0f)) {
                 const float alpha = fminf(GS_ALPHA_MAX, fmul(q1.w, gs_exp(power)));
                 if (!(alpha < GS_ALPHA_MIN)) {
@@ -273,6 +320,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
         g0_c = make_float4(0.f, 0.f, -1.f, -1.f);
         if (hi - 33 - lane >= 0) g0_c = __ldg(recs4 + 3 * (size_t)id_c);
         if (hi - 65 - lane >= 0) id_n = __ldg(plist + (hi - 65 - lane));
+#ifdef BLEND_COUNTERS
+        CNT_ADD(8, 1); CNT_ADD(9, min(32, hi)); CNT_ADD(10, __popc(b));
+        CNT_ADD(11, __popc(__ballot_sync(FULL, hit && ellipse_hits_patch(g0_h, g1, fx0, fy0))));
+#endif
         if (b == 0u) continue;
         if (hit) {
             const int s = __popc(b & lt);
@@ -292,6 +343,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
             const float G = gs_exp(power);
             const float alpha = fminf(GS_ALPHA_MAX, fmul(q1.w, G));
             const bool contrib = (pos < last) && !(power > 0.0f) && !(alpha < GS_ALPHA_MIN);
+#ifdef BLEND_COUNTERS
+            {
+                const uint32_t bc = __ballot_sync(FULL, contrib);
+                CNT_ADD(12, bc != 0u); CNT_ADD(13, __popc(bc)); CNT_ADD(15, bc != 0u && __popc(bc) < 8);
+            }
+#endif
             if (!__any_sync(FULL, contrib)) continue;
             float q = 0.f, w = 0.f;
             if (contrib) {

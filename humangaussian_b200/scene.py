@@ -10,6 +10,7 @@ their statistics follow SURVEY.md 8(c)/(d).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -209,6 +210,39 @@ def synthetic_body(P, sh_degree=0, seed=0, surface=True):
     fdc = (torch.randn(P, 1, 3, generator=g) * 1.1)
     rest = torch.randn(P, K - 1, 3, generator=g) * 0.1
     return GaussianParams(xyz.float(), fdc.float(), rest.float(), scaling.float(), rot.float(), opacity.float(), sh_degree)
+
+
+SAMPLE_COLUMNS = ("x", "y", "z", "f_dc_0", "f_dc_1", "f_dc_2", "opacity", "scale_0", "scale_1", "scale_2",
+                  "rot_0", "rot_1", "rot_2", "rot_3")
+SAMPLE_NPZ = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "sample_ply_full.npz")
+
+
+def sample_ply_scene(n=None, sh_degree=0, seed=0, convention="training", path=None):
+    """The reference's own scene, content/sample.ply (531 327 Gaussians, SH degree 0), from the committed column pack
+    tests/golden/sample_ply_full.npz (tests/golden/make_sample_scene.py) -- BASELINE configs 2, 4, 5.
+    n: keep a seed-`seed` subsample of n Gaussians (n = 300 000, seed 0); sh_degree > 0 widens with
+    f_rest ~ N(0, 0.1^2) (seed `seed`), as 8d prescribes.  Raw (pre-activation) parameters, like load_ply
+    (gaussiansplatting/scene/gaussian_model.py:225-266); convention="animation" applies gs_renderer.py:576-581."""
+    z = np.load(path or SAMPLE_NPZ)
+    d = z["data"]
+    col = {k: d[:, i] for i, k in enumerate(SAMPLE_COLUMNS)}
+    xyz = np.stack([col["x"], col["y"], col["z"]], 1)
+    fdc = np.stack([col["f_dc_0"], col["f_dc_1"], col["f_dc_2"]], 1)[:, None, :]
+    scales = np.stack([col["scale_0"], col["scale_1"], col["scale_2"]], 1)
+    rots = np.stack([col["rot_0"], col["rot_1"], col["rot_2"], col["rot_3"]], 1)
+    if convention == "animation":
+        xyz, scales = xyz[:, [0, 2, 1]], scales[:, [0, 2, 1]]
+        rots = rots[:, [0, 1, 3, 2]].copy()
+        rots[:, 0] *= -1
+    elif convention != "training":
+        raise ValueError(convention)
+    t = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float32)
+    p = GaussianParams(t(xyz), t(fdc), torch.zeros(len(xyz), 0, 3), t(scales), t(rots), t(col["opacity"][:, None]), 0)
+    if n is not None and n < p.P:
+        p = subsample(p, n, seed)
+    if sh_degree > 0:
+        p = with_sh_degree(p, sh_degree, seed)
+    return p
 
 
 def subsample(p: GaussianParams, n, seed=0):
