@@ -128,15 +128,18 @@ int b200gs_forward(const b200gs_params *prm, const float *means3D, const float *
         uint32_t *offsets = (uint32_t *)(gb + GL.offsets); // inclusive scan of tiles_touched in DEPTH order
         const int64_t n_vp = (int64_t)P * V;
         const uint32_t *order_sorted = nullptr;
+        const uint64_t *total_dev = nullptr;
         int nl = 0;
         {
             StageTimer t(B200GS_STAGE_SCAN, st);
-            if (launch_depth_order(a.tiles_touched, offsets, n_vp, V, bb, BL, &order_sorted, st, &nl)) return cuda_fail(cudaGetLastError(), "depth order");
+            if (launch_depth_order(a.tiles_touched, offsets, n_vp, V, bb, BL, &order_sorted, &total_dev, st, &nl)) return cuda_fail(cudaGetLastError(), "depth order");
         }
-        uint32_t total = 0;
-        CK(cudaMemcpyAsync(&total, offsets + (n_vp - 1), 4, cudaMemcpyDeviceToHost, st), "D2H num_rendered");
+        // the EXACT 64-bit instance count (the 32-bit offsets may have wrapped: nothing reads them before this check)
+        uint64_t total = 0;
+        CK(cudaMemcpyAsync(&total, total_dev, 8, cudaMemcpyDeviceToHost, st), "D2H num_rendered");
         CK(cudaStreamSynchronize(st), "sync after scan");
         *num_rendered = (int64_t)total;
+        if (total > (uint64_t)B200GS_MAX_INSTANCES) return B200GS_E_INSTANCES;
         if ((int64_t)total > instance_capacity) return B200GS_E_BIN_TOO_SMALL;
         {
             StageTimer t(B200GS_STAGE_BINNING, st);

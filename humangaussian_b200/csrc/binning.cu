@@ -97,9 +97,10 @@ static int radix_sort_pairs(KeyT *ka, KeyT *kb, uint32_t *va, uint32_t *vb, int6
 }
 
 // depth pre-sort + scan in depth order.  dkeys_in / order_in were written by the preprocess kernel.
-// On return *order_sorted points at the sorted record indices (inside bin_base).
+// On return *order_sorted points at the sorted record indices (inside bin_base) and *total_dev at the exact 64-bit
+// instance count of the batch (device word, valid once the stream reaches this point).
 int launch_depth_order(const uint32_t *tiles_touched, uint32_t *offsets_sorted, int64_t n_vp, int V, char *bin_base,
-                       const BinLayout &L, const uint32_t **order_sorted, cudaStream_t st, int *n_launches)
+                       const BinLayout &L, const uint32_t **order_sorted, const uint64_t **total_dev, cudaStream_t st, int *n_launches)
 {
     uint32_t *ks = nullptr, *vs = nullptr;
     if (radix_sort_pairs<uint32_t, D_BITS, D_IPT>((uint32_t *)(bin_base + L.dkeys_in), (uint32_t *)(bin_base + L.dkeys_out),
@@ -111,7 +112,8 @@ int launch_depth_order(const uint32_t *tiles_touched, uint32_t *offsets_sorted, 
     char *scr = bin_base + L.temp;
     cudaMemsetAsync(scr, 0, gs_align((nblocks + 1) * 8) + 256, st);
     scan_tiles_kernel<<<(unsigned)nblocks, THREADS, 0, st>>>(vs, tiles_touched, offsets_sorted, n_vp, (volatile uint64_t *)(scr + 256),
-                                                            (uint32_t *)scr);
+                                                            (uint32_t *)scr, (uint64_t *)(scr + 8));
+    *total_dev = (const uint64_t *)(scr + 8);
     *n_launches += 1;
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
 }
@@ -253,7 +255,7 @@ int launch_binning(const uint32_t *order_sorted, const uint2 *rects, const uint3
         *n_launches += 2;
         return 0;
     }
-    if (D >= ((int64_t)1 << 30)) return -3; // look-back status words carry 30-bit counts
+    if (D > B200GS_MAX_INSTANCES_I64) return -3; // api.cu rejects this before calling; 32-bit instance indices end here
     const int nbits = bits_for((uint64_t)ntiles * V) > 0 ? bits_for((uint64_t)ntiles * V) : 1;
     const int npass = (nbits + T_BITS - 1) / T_BITS;
     // emit into the buffer from which `npass` ping-pong passes end in keys_out/vals_out

@@ -221,9 +221,11 @@ __global__ void __launch_bounds__(THREADS) scatter_kernel(const KeyT *__restrict
 constexpr int SCAN_IPT = 8;
 __global__ void __launch_bounds__(THREADS) scan_tiles_kernel(const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
                                                               uint32_t *__restrict__ out, int64_t n, volatile uint64_t *status /* [nblocks], zeroed */,
-                                                              uint32_t *ticket /* zeroed */)
+                                                              uint32_t *ticket /* zeroed */, uint64_t *total_out /* exact 64-bit sum */)
 {
-    // status: bit 63 = prefix ready, bit 62 = aggregate ready, low 40 bits = value
+    // status: bit 63 = prefix ready, bit 62 = aggregate ready, low 56 bits = value (the exact running sum: V*P < 2^32
+    // entries of at most 2^24 tiles each cannot reach 2^56).  out[] keeps the low 32 bits; the host rejects a batch whose
+    // exact total does not fit BEFORE anything is emitted (api.cu).
     constexpr int TILE = THREADS * SCAN_IPT;
     __shared__ uint32_t s_bid, s_wsum[WARPS];
     __shared__ uint64_t s_excl;
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(THREADS) scan_tiles_kernel(const uint32_t *__r
         total += s_wsum[w];
     }
     if (tid == 0) {
-        const uint64_t AGG = 1ull << 62, PRE = 1ull << 63, VM = (1ull << 40) - 1;
+        const uint64_t AGG = 1ull << 62, PRE = 1ull << 63, VM = (1ull << 56) - 1;
         status[bid] = (bid == 0 ? PRE : AGG) | (uint64_t)total;
         __threadfence();
         uint64_t excl = 0;
@@ -268,6 +270,7 @@ __global__ void __launch_bounds__(THREADS) scan_tiles_kernel(const uint32_t *__r
             }
             status[bid] = PRE | (excl + total);
         }
+        if ((int64_t)(bid + 1) * TILE >= n) *total_out = excl + total; // the block holding the last element
         s_excl = excl;
     }
     __syncthreads();

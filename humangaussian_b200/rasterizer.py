@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from typing import NamedTuple, Optional
 
 import torch
@@ -29,8 +30,19 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200GS_LIB") or os.path.join(_HERE, "libb200gs.so")
 ABI_VERSION = 2
 MAX_VIEWS = 64
+MAX_INSTANCES = 0x7FFFFFFF  # (Gaussian, tile) instances per call (B200GS_MAX_INSTANCES); larger batches are split by views
 
-OK, E_ARGS, E_BIN_TOO_SMALL, E_BUFFER, E_CUDA, E_RANGE = 0, -1, -2, -3, -4, -5
+OK, E_ARGS, E_BIN_TOO_SMALL, E_BUFFER, E_CUDA, E_RANGE, E_INSTANCES = 0, -1, -2, -3, -4, -5, -6
+
+
+class InstanceLimitError(RuntimeError):
+    """The view batch has more (Gaussian, tile) instances than one call supports (B200GS_E_INSTANCES).  `rasterize_views`
+    catches it and renders the batch in two halves; a single view that exceeds the limit propagates it."""
+
+    def __init__(self, count):
+        super().__init__(f"b200gs: {count} (Gaussian, tile) instances in one call exceed the supported {MAX_INSTANCES}; "
+                         "render fewer views per call")
+        self.count = count
 
 
 class _Params(C.Structure):
@@ -129,6 +141,7 @@ def _check(rc, what):
         return
     L = load_library()
     msg = {E_ARGS: "inconsistent arguments", E_BUFFER: "state buffer too small", E_RANGE: "size outside supported range",
+           E_INSTANCES: "too many (Gaussian, tile) instances in one call",
            E_CUDA: "CUDA error: " + (L.b200gs_last_cuda_error() or b"").decode()}.get(rc, f"status {rc}")
     raise RuntimeError(f"b200gs {what} failed: {msg}")
 
@@ -161,7 +174,8 @@ def _stream(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-# instance-capacity hint per (device, P, V, H, W): avoids the retry after the first call
+# instance-capacity hint per (device, P, V, H, W): the largest count seen so far (+25 %), so that after the first few
+# cameras a call neither retries nor re-sizes its binning buffer
 _cap_hint: dict = {}
 
 
@@ -173,9 +187,49 @@ def last_num_rendered() -> int:
     return _last_num_rendered
 
 
+class _StatePool:
+    """Free lists of the opaque state buffers (geom | image | binning | backward scratch), keyed by (device, stream, sizes).
+    A forward checks a set out, its autograd ctx holds it until the graph is freed, then the set returns here instead of
+    going back to the allocator: the per-view calling pattern (GaussianDreamer.py:244-248) re-uses the same few sets every
+    step.  Bounded: at most `max_bytes` are parked; anything beyond is simply dropped (freed by torch)."""
+
+    def __init__(self, max_bytes=24 << 30):
+        self.free: dict = {}
+        self.parked = 0
+        self.max_bytes = max_bytes
+
+    def take(self, key):
+        lst = self.free.get(key)
+        if lst:
+            bufs = lst.pop()
+            self.parked -= sum(b.numel() for b in bufs.values())
+            return bufs
+        return None
+
+    def give(self, key, bufs):
+        n = sum(b.numel() for b in bufs.values())
+        if self.parked + n > self.max_bytes:
+            return
+        self.free.setdefault(key, []).append(bufs)
+        self.parked += n
+
+    def clear(self):
+        self.free.clear()
+        self.parked = 0
+
+
+_pool = _StatePool()
+
+
+def release_cached_buffers():
+    """Drop the parked state buffers (e.g. after densification changed P)."""
+    _pool.clear()
+
+
 class _Ctx:
     """What one forward keeps for its backward (upstream keeps geomBuffer/binningBuffer/imgBuffer the same way)."""
-    __slots__ = ("prm", "tanx", "tany", "geom", "binning", "image", "capacity", "num_rendered", "radii", "V", "P", "H", "W", "M")
+    __slots__ = ("prm", "tanx", "tany", "geom", "binning", "image", "scratch", "capacity", "num_rendered", "radii", "V", "P", "H",
+                 "W", "M", "__weakref__")
 
 
 def _make_params(P, V, deg, M, H, W, mod, tanx, tany, prefiltered=False, debug=False, per_view_means=False):
@@ -206,8 +260,6 @@ def _forward_impl(means3D, shs, colors_precomp, opacities, scales, rotations, co
     M = 0 if shs is None else shs.shape[1]
     prm, tx, ty = _make_params(P, V, sh_degree, M, H, W, scale_modifier, tanfovx, tanfovy, prefiltered, debug, per_view_means)
     u8 = dict(dtype=torch.uint8, device=dev)
-    geom = torch.empty(L.b200gs_geom_bytes(P, V), **u8)
-    image = torch.empty(L.b200gs_image_bytes(H, W, V), **u8)
     color = torch.empty(V, 3, H, W, dtype=torch.float32, device=dev)
     depth = torch.empty(V, 1, H, W, dtype=torch.float32, device=dev)
     alpha = torch.empty(V, 1, H, W, dtype=torch.float32, device=dev)
@@ -215,24 +267,36 @@ def _forward_impl(means3D, shs, colors_precomp, opacities, scales, rotations, co
     key = (dev.index, P, V, H, W)
     cap = _cap_hint.get(key, max(1 << 16, 4 * P * V))
     n_out = C.c_int64(0)
+    stream = torch.cuda.current_stream(dev).cuda_stream
     with torch.cuda.device(dev):
         for _ in range(3):
-            binning = torch.empty(L.b200gs_binning_bytes(cap, H, W, P, V), **u8)
+            pkey = (key, stream, cap)
+            bufs = _pool.take(pkey)
+            if bufs is None:
+                bufs = dict(geom=torch.empty(L.b200gs_geom_bytes(P, V), **u8), image=torch.empty(L.b200gs_image_bytes(H, W, V), **u8),
+                            binning=torch.empty(L.b200gs_binning_bytes(cap, H, W, P, V), **u8),
+                            scratch=torch.empty(max(L.b200gs_backward_scratch_bytes(P, V), 16), **u8))
+            geom, image, binning = bufs["geom"], bufs["image"], bufs["binning"]
             rc = L.b200gs_forward(C.byref(prm), _ptr(means3D), _ptr(shs), _ptr(colors_precomp), _ptr(opacities), _ptr(scales),
                                   _ptr(rotations), _ptr(cov3D_precomp), _ptr(bg), _ptr(viewmatrix), _ptr(projmatrix),
                                   _ptr(campos), _ptr(color), _ptr(depth), _ptr(alpha), _ptr(radii), _ptr(geom), geom.numel(),
-                                  _ptr(binning), binning.numel(), cap, _ptr(image), image.numel(), C.byref(n_out), _stream(dev))
+                                  _ptr(binning), binning.numel(), cap, _ptr(image), image.numel(), C.byref(n_out), C.c_void_p(stream))
+            if rc == OK and n_out.value > MAX_INSTANCES:  # (the library applies the same limit; this one can be lowered in tests)
+                rc = E_INSTANCES
             if rc != E_BIN_TOO_SMALL:
                 break
             cap = int(n_out.value * 1.25) + 1024
+        if rc == E_INSTANCES:
+            raise InstanceLimitError(int(n_out.value))
         _check(rc, "forward")
-    _cap_hint[key] = max(int(n_out.value * 1.25) + 1024, 1 << 16)
+    _cap_hint[key] = max(int(n_out.value * 1.25) + 1024, 1 << 16, _cap_hint.get(key, 0))
     global _last_num_rendered
     _last_num_rendered = int(n_out.value)
     st = _Ctx()
     st.prm, st.tanx, st.tany = prm, tx, ty
-    st.geom, st.binning, st.image, st.capacity, st.num_rendered = geom, binning, image, cap, int(n_out.value)
+    st.geom, st.binning, st.image, st.scratch, st.capacity, st.num_rendered = geom, binning, image, bufs["scratch"], cap, int(n_out.value)
     st.radii, st.V, st.P, st.H, st.W, st.M = radii, V, P, H, W, M
+    weakref.finalize(st, _pool.give, pkey, bufs)  # when the autograd graph drops the state, the buffers are parked for re-use
     return color, radii, depth, alpha, st
 
 
@@ -255,7 +319,7 @@ def _backward_impl(st: _Ctx, means3D, shs, colors_precomp, opacities, scales, ro
     d_cov = torch.empty(P, 6, **f) if cov3D_precomp is not None else None
     if P == 0:
         return d_means3D, d_means2D, d_sh, d_col, d_op, d_sc, d_rot, d_cov
-    scratch = torch.empty(L.b200gs_backward_scratch_bytes(P, V), dtype=torch.uint8, device=dev)
+    scratch = st.scratch
     with torch.cuda.device(dev):
         rc = L.b200gs_backward(C.byref(st.prm), _ptr(means3D), _ptr(shs), _ptr(colors_precomp), _ptr(opacities), _ptr(scales),
                                _ptr(rotations), _ptr(cov3D_precomp), _ptr(bg), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos),
@@ -265,6 +329,18 @@ def _backward_impl(st: _Ctx, means3D, shs, colors_precomp, opacities, scales, ro
                                _stream(dev))
     _check(rc, "backward")
     return d_means3D, d_means2D, d_sh, d_col, d_op, d_sc, d_rot, d_cov
+
+
+def _save(ctx, tensors):
+    """save_for_backward with None holes: autograd's version counters then catch an in-place update of a parameter
+    between forward and backward (the saved tensors are the caller's own storage whenever it already was contiguous fp32)."""
+    ctx.none_mask = [t is None for t in tensors]
+    ctx.save_for_backward(*[t for t in tensors if t is not None])
+
+
+def _saved(ctx):
+    it = iter(ctx.saved_tensors)
+    return [None if m else next(it) for m in ctx.none_mask]
 
 
 class _RasterizeViews(torch.autograd.Function):
@@ -278,7 +354,7 @@ class _RasterizeViews(torch.autograd.Function):
         camt = [_f32c(t, dev) for t in (bg, viewmatrix, projmatrix, campos)]
         color, radii, depth, alpha, st = _forward_impl(*args, *camt, tanx, tany, H, W, deg, mod, prefiltered, debug)
         ctx.st, ctx.squeeze = st, squeeze
-        ctx.saved = args + camt  # plain references: these are detached copies or the caller's own storage
+        _save(ctx, args + camt)
         ctx.in_shapes = [None if t is None else t.shape for t in (means3D, means2D, shs, colors_precomp, opacities, scales,
                                                                   rotations, cov3D_precomp)]
         ctx.mark_non_differentiable(radii)
@@ -288,16 +364,14 @@ class _RasterizeViews(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_color, g_radii, g_depth, g_alpha):
-        st = ctx.st
-        means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, viewmatrix, projmatrix, campos = ctx.saved
+        st = ctx.st  # kept until the graph is freed: a second backward (retain_graph=True) recomputes from the same state
+        means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, viewmatrix, projmatrix, campos = _saved(ctx)
         dev = means3D.device
         g = [None if t is None else _f32c(t, dev) for t in (g_color, g_depth, g_alpha)]
         d_means3D, d_means2D, d_sh, d_col, d_op, d_sc, d_rot, d_cov = _backward_impl(
             st, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, viewmatrix, projmatrix, campos, *g)
         if ctx.squeeze:
             d_means2D = d_means2D[0]
-        ctx.st = None
-        ctx.saved = None
         # gradients take the shape the caller passed (e.g. opacities [P] or [P,1])
         grads = [g if (g is None or shp is None) else g.reshape(shp)
                  for g, shp in zip((d_means3D, d_means2D, d_sh, d_col, d_op, d_sc, d_rot, d_cov), ctx.in_shapes)]
@@ -380,7 +454,19 @@ def rasterize_views(*, means3D, opacities, viewmatrices, projmatrices, camposs, 
         means2D = torch.zeros(V, means3D.shape[-2], 3, dtype=torch.float32, device=means3D.device)
     cams = (bg, viewmatrices, projmatrices, camposs, list(tanfovx), list(tanfovy), int(image_height), int(image_width),
             int(sh_degree), float(scale_modifier), False, False)
-    return _RasterizeViews.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, cams, False)
+    try:
+        return _RasterizeViews.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, cams, False)
+    except InstanceLimitError:
+        if V == 1:
+            raise
+    # more (Gaussian, tile) instances than one call supports: render the two halves of the view batch and concatenate
+    h = V // 2
+    outs = [rasterize_views(means3D=means3D if means3D.dim() == 2 else means3D[sl], opacities=opacities, viewmatrices=viewmatrices[sl],
+                            projmatrices=projmatrices[sl], camposs=camposs[sl], tanfovx=list(tanfovx)[sl], tanfovy=list(tanfovy)[sl],
+                            image_height=image_height, image_width=image_width, bg=bg, sh_degree=sh_degree, shs=shs,
+                            colors_precomp=colors_precomp, scales=scales, rotations=rotations, cov3D_precomp=cov3D_precomp,
+                            means2D=means2D[sl], scale_modifier=scale_modifier) for sl in (slice(0, h), slice(h, V))]
+    return tuple(torch.cat([o[k] for o in outs], 0) for k in range(4))
 
 
 # ---- packed entry: one flat SoA parameter buffer in, one flat gradient buffer out ---------------------------------
@@ -415,13 +501,15 @@ class _RasterizePacked(torch.autograd.Function):
         xyz, sc, rot, op, sh = _split_packed(packed.detach(), P, M)
         camt = [_f32c(t, dev) for t in (bg, viewmatrix, projmatrix, campos)]
         color, radii, depth, alpha, st = _forward_impl(xyz, sh, None, op, sc, rot, None, *camt, tanx, tany, H, W, deg, mod)
-        ctx.st, ctx.saved, ctx.P, ctx.M = st, [packed.detach()] + camt, P, M
+        ctx.st, ctx.P, ctx.M = st, P, M
+        ctx.save_for_backward(packed, *camt)
         ctx.mark_non_differentiable(radii)
         return color, radii, depth, alpha
 
     @staticmethod
     def backward(ctx, g_color, g_radii, g_depth, g_alpha):
-        packed, bg, viewmatrix, projmatrix, campos = ctx.saved
+        packed, bg, viewmatrix, projmatrix, campos = ctx.saved_tensors
+        packed = packed.detach()
         P, M, dev = ctx.P, ctx.M, packed.device
         xyz, sc, rot, op, sh = _split_packed(packed, P, M)
         d_packed = torch.empty_like(packed) if P % 4 == 0 else torch.zeros_like(packed)  # alignment padding carries zero gradient
@@ -429,7 +517,6 @@ class _RasterizePacked(torch.autograd.Function):
         g = [None if t is None else _f32c(t, dev) for t in (g_color, g_depth, g_alpha)]
         _, d_means2D, *_ = _backward_impl(ctx.st, xyz, sh, None, op, sc, rot, None, bg, viewmatrix, projmatrix, campos, *g,
                                           out=dict(means3D=d_xyz, sh=d_sh, opacity=d_op, scales=d_sc, rotations=d_rot))
-        ctx.st = ctx.saved = None
         return d_packed, d_means2D, None, None, None
 
 
@@ -452,7 +539,17 @@ def rasterize_views_packed(packed: torch.Tensor, P: int, sh_coeffs: int, *, view
         means2D = torch.zeros(V, P, 3, dtype=torch.float32, device=packed.device)
     cams = (bg, viewmatrices, projmatrices, camposs, list(tanfovx), list(tanfovy), int(image_height), int(image_width),
             int(sh_degree), float(scale_modifier))
-    return _RasterizePacked.apply(packed, means2D, int(P), int(sh_coeffs), cams)
+    try:
+        return _RasterizePacked.apply(packed, means2D, int(P), int(sh_coeffs), cams)
+    except InstanceLimitError:
+        if V == 1:
+            raise
+    h = V // 2  # too many instances for one call: two half batches; autograd sums the two packed gradients
+    outs = [rasterize_views_packed(packed, P, sh_coeffs, viewmatrices=viewmatrices[sl], projmatrices=projmatrices[sl], camposs=camposs[sl],
+                                   tanfovx=list(tanfovx)[sl], tanfovy=list(tanfovy)[sl], image_height=image_height,
+                                   image_width=image_width, bg=bg, sh_degree=sh_degree, means2D=means2D[sl],
+                                   scale_modifier=scale_modifier) for sl in (slice(0, h), slice(h, V))]
+    return tuple(torch.cat([o[k] for o in outs], 0) for k in range(4))
 
 
 # ---- test / debugging access to the forward state (tile and sort indices) -----------------------------------

@@ -60,13 +60,31 @@ def stack_cameras(cameras, device):
     return vm, pm, cp, tanx, tany
 
 
+class _StackSinks(torch.autograd.Function):
+    """[V,P,3] view-batch gradient sink whose backward hands row v to the v-th per-view sink (a leaf [P,3] tensor), so that
+    `sink.grad` is filled exactly as the per-view loop fills `viewspace_point_tensor.grad` (GaussianDreamer.py:249-250,
+    385-387).  The sinks alias `base` (all zeros, never written): forward copies nothing."""
+
+    @staticmethod
+    def forward(ctx, base, *sinks):
+        return base.view_as(base)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None, *g.unbind(0))
+
+
 def render_views(cameras, pc, bg_color, scaling_modifier=1.0):
     """All cameras share image size.  Returns the dict of `render` with a leading view axis:
-    render [V,3,H,W], depth_3dgs/alpha_3dgs [V,1,H,W], radii [V,P], viewspace_points [V,P,3]."""
+    render [V,3,H,W], depth_3dgs/alpha_3dgs [V,1,H,W], radii [V,P], viewspace_points [V,P,3] (its .grad is [V,P,3]),
+    plus viewspace_point_list: V leaf tensors [P,3] whose .grad backward fills -- what the reference's
+    `self.viewspace_point_list` holds (GaussianDreamer.py:242-250) and on_before_optimizer_step sums (:385-387)."""
     xyz = pc.get_xyz
     V = len(cameras)
     vm, pm, cp, tanx, tany = stack_cameras(cameras, xyz.device)
-    screenspace_points = torch.zeros(V, xyz.shape[0], 3, dtype=xyz.dtype, device=xyz.device, requires_grad=True) + 0
+    base = torch.zeros(V, xyz.shape[0], 3, dtype=torch.float32, device=xyz.device)
+    sinks = [t.requires_grad_(True) for t in base.unbind(0)]
+    screenspace_points = _StackSinks.apply(base, *sinks)
     try:
         screenspace_points.retain_grad()
     except Exception:
@@ -76,5 +94,5 @@ def render_views(cameras, pc, bg_color, scaling_modifier=1.0):
         image_height=int(cameras[0].image_height), image_width=int(cameras[0].image_width), bg=bg_color,
         sh_degree=pc.active_sh_degree, shs=pc.get_features, scales=pc.get_scaling, rotations=pc.get_rotation,
         means2D=screenspace_points, scale_modifier=scaling_modifier)
-    return {"render": image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii,
-            "depth_3dgs": depth, "alpha_3dgs": alpha}
+    return {"render": image, "viewspace_points": screenspace_points, "viewspace_point_list": sinks, "visibility_filter": radii > 0,
+            "radii": radii, "depth_3dgs": depth, "alpha_3dgs": alpha}

@@ -118,8 +118,12 @@ class GaussianParams:
         return self.sh_degree
 
 
-def _sorted_cols(cols, prefix):
-    names = sorted((k for k in cols if k.startswith(prefix)), key=lambda s: int(s.split("_")[-1]))
+def _sorted_cols(cols, prefix, sort=True):
+    """Columns whose name starts with `prefix`, in index order (training loader: gaussian_model.py:241-263 sorts by the
+    trailing integer) or in FILE order (animation loader: gs_renderer.py:553-576 does not sort)."""
+    names = [k for k in cols if k.startswith(prefix)]
+    if sort:
+        names = sorted(names, key=lambda s: int(s.split("_")[-1]))
     return np.stack([cols[k] for k in names], axis=1) if names else np.zeros((len(cols["x"]), 0), np.float32)
 
 
@@ -127,22 +131,23 @@ def params_from_ply(path, sh_degree=0, convention="training"):
     """convention="training": gaussian_model.py:225-266 (z-up as stored).
     convention="animation": gs_renderer.py:576-581 (swap y/z of xyz and scales, swap quaternion
     comps 2/3 and negate comp 0)."""
+    if convention not in ("training", "animation"):
+        raise ValueError(convention)
     c = read_ply(path)
+    srt = convention == "training"
     xyz = np.stack([c["x"], c["y"], c["z"]], axis=1)
     fdc = np.stack([c["f_dc_0"], c["f_dc_1"], c["f_dc_2"]], axis=1)[:, None, :]
     K = (sh_degree + 1) ** 2
-    rest = _sorted_cols(c, "f_rest_")
+    rest = _sorted_cols(c, "f_rest_", srt)
     if rest.shape[1] != 3 * K - 3:
         raise ValueError(f"PLY has {rest.shape[1]} f_rest_* columns, sh_degree={sh_degree} needs {3 * K - 3}")
     rest = rest.reshape(len(xyz), 3, K - 1).transpose(0, 2, 1)
-    scales, rots = _sorted_cols(c, "scale_"), _sorted_cols(c, "rot")
+    scales, rots = _sorted_cols(c, "scale_", srt), _sorted_cols(c, "rot", srt)
     if convention == "animation":
         xyz = xyz[:, [0, 2, 1]]
         scales = scales[:, [0, 2, 1]]
         rots = rots[:, [0, 1, 3, 2]].copy()
         rots[:, 0] *= -1
-    elif convention != "training":
-        raise ValueError(convention)
     t = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float32)
     return GaussianParams(t(xyz), t(fdc), t(rest), t(scales), t(rots), t(c["opacity"][:, None]), sh_degree)
 

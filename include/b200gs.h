@@ -41,8 +41,11 @@ typedef enum b200gs_status {
     B200GS_E_BIN_TOO_SMALL = -2, /* binning buffer cannot hold the instances; *num_rendered holds the count needed: grow and call again */
     B200GS_E_BUFFER = -3,        /* a state buffer is smaller than b200gs_*_bytes() asks for */
     B200GS_E_CUDA = -4,          /* a CUDA call failed; see b200gs_last_cuda_error() */
-    B200GS_E_RANGE = -5          /* sizes outside supported range (sh_degree > 3, n_views > B200GS_MAX_VIEWS, > 2^32-1 instances) */
+    B200GS_E_RANGE = -5,         /* sizes outside supported range (sh_degree > 3, n_views > B200GS_MAX_VIEWS, P*V >= 2^32, > 65535 tiles per axis) */
+    B200GS_E_INSTANCES = -6      /* the batch has more than B200GS_MAX_INSTANCES (Gaussian, tile) instances; *num_rendered holds the exact
+                                    64-bit count; nothing was emitted: render fewer views per call (the host mirror halves the batch) */
 } b200gs_status;
+#define B200GS_MAX_INSTANCES 0x7fffffffLL
 
 /* Mirrors GaussianRasterizationSettings (12 fields; built at gaussian_renderer/__init__.py:36-49) plus sizes.
  * tanfovx/tanfovy are per view (host arrays) because every camera of an SDS batch has its own fovy

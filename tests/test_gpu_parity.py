@@ -270,3 +270,54 @@ def test_real_scene_512_config2():
     assert o_st["num_rendered"] > 20000 and (o_out[1] > 0).all()
     _check_forward_state(inp, o_out, o_st)
     _check_backward(inp, o_out, gimg, o_grads)
+
+
+def test_render_views_feeds_reference_optimizer_hook():
+    """render_views' `viewspace_point_list` must let the reference's on_before_optimizer_step
+    (threestudio/systems/GaussianDreamer.py:385-391) run unchanged, and give what the per-view loop (:244-256) gives."""
+    from humangaussian_b200.cameras import sample_orbit_cameras
+    from humangaussian_b200.renderer import PipelineParams, render, render_views
+    from humangaussian_b200.scene import synthetic_body
+    H = W = 96
+    cams = sample_orbit_cameras(4, H, W, seed=3, device=DEV)
+    bg = torch.zeros(3, device=DEV)
+    g = torch.Generator(device=DEV).manual_seed(0)
+    wts = torch.randn(4, 3, H, W, device=DEV, generator=g)
+
+    def fresh():
+        p = synthetic_body(3000, sh_degree=1, seed=2)
+        p.scaling += math.log(5.0)
+        p = p.to(DEV)
+        for t in (p.xyz, p.features_dc, p.features_rest, p.scaling, p.rotation, p.opacity):
+            t.requires_grad_(True)
+        return p
+
+    # the reference's loop (:244-256) ...
+    pa = fresh()
+    vlist, radii, loss = [], None, 0
+    for i, cam in enumerate(cams):
+        pkg = render(cam, pa, PipelineParams(), bg)
+        vlist.append(pkg["viewspace_points"])
+        radii = pkg["radii"] if radii is None else torch.max(pkg["radii"], radii)
+        loss = loss + (pkg["render"] * wts[i]).sum() + pkg["depth_3dgs"].sum()
+    loss.backward()
+    # ... and its hook body (:385-387), verbatim
+    grad_ref = torch.zeros_like(vlist[0])
+    for idx in range(len(vlist)):
+        grad_ref = grad_ref + vlist[idx].grad
+    # the batched wiring
+    pb = fresh()
+    pkg = render_views(cams, pb, bg)
+    viewspace_point_list = pkg["viewspace_point_list"]
+    ((pkg["render"] * wts).sum() + pkg["depth_3dgs"].sum()).backward()
+    viewspace_point_tensor_grad = torch.zeros_like(viewspace_point_list[0])
+    for idx in range(len(viewspace_point_list)):
+        viewspace_point_tensor_grad = viewspace_point_tensor_grad + viewspace_point_list[idx].grad
+    assert viewspace_point_tensor_grad.shape == (3000, 3)
+    ok, worst = close(viewspace_point_tensor_grad.cpu().numpy(), grad_ref.cpu().numpy())
+    assert ok, worst
+    assert torch.equal(pkg["radii"].max(0).values, radii)
+    assert torch.equal(pkg["viewspace_points"].grad.sum(0), viewspace_point_tensor_grad) or \
+        close(pkg["viewspace_points"].grad.sum(0).cpu().numpy(), viewspace_point_tensor_grad.cpu().numpy())[0]
+    ok, worst = close(pb.xyz.grad.cpu().numpy(), pa.xyz.grad.cpu().numpy())
+    assert ok, worst

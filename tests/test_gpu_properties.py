@@ -251,3 +251,57 @@ def test_odd_P_and_misaligned_pointers():
     gp = unpack(flat.grad, P, K)
     assert float((gp["rotation"] - a["rotations"].grad).abs().max()) <= 1e-6 + 1e-5 * float(a["rotations"].grad.abs().max())
     assert float((gp["features"] - a["shs"].grad).abs().max()) <= 1e-6 + 1e-5 * float(a["shs"].grad.abs().max())
+
+
+def _screen_fillers(P, V, HW):
+    from humangaussian_b200.cameras import sample_orbit_cameras
+    from humangaussian_b200.renderer import stack_cameras
+    g = torch.Generator().manual_seed(0)
+    xyz = (torch.randn(P, 3, generator=g) * 0.05).to(DEV)
+    sc = torch.full((P, 3), 40.0, device=DEV)          # world-space sigma of 40 units: every Gaussian covers every tile
+    rot = torch.tensor([1.0, 0, 0, 0], device=DEV).repeat(P, 1)
+    op = torch.full((P, 1), 0.02, device=DEV)
+    sh = torch.zeros(P, 1, 3, device=DEV)
+    cams = sample_orbit_cameras(V, HW, HW, seed=5, device=DEV)
+    return xyz, sc, rot, op, sh, stack_cameras(cams, DEV)
+
+
+def test_instance_count_beyond_32_bits_is_refused_not_wrapped():
+    """64 views x 16384 screen-filling Gaussians x 4096 tiles = 2^32 instances: the 32-bit scan wraps to 0.  The library
+    must report the exact 64-bit count and refuse (B200GS_E_INSTANCES) before anything is emitted."""
+    from humangaussian_b200 import rasterizer as R
+    P, V, HW = 16384, 64, 1024
+    xyz, sc, rot, op, sh, (vm, pm, cp, tanx, tany) = _screen_fillers(P, V, HW)
+    with pytest.raises(R.InstanceLimitError) as e:
+        R._forward_impl(xyz, sh, None, op, sc, rot, None, torch.zeros(3, device=DEV), vm, pm, cp, tanx, tany, HW, HW, 0, 1.0)
+    assert e.value.count == P * V * 4096 == 1 << 32
+    torch.cuda.synchronize()
+
+
+def test_view_batch_is_halved_when_the_instance_limit_is_hit(monkeypatch):
+    """rasterize_views splits the batch on InstanceLimitError; results equal the unsplit call (limit lowered for the test)."""
+    from humangaussian_b200 import rasterizer as R
+    P, V, HW = 300, 8, 128
+    xyz, sc, rot, op, sh, (vm, pm, cp, tanx, tany) = _screen_fillers(P, V, HW)
+    bg = torch.tensor([0.2, 0.3, 0.4], device=DEV)
+    gw = torch.randn(V, 3, HW, HW, device=DEV)
+
+    def run():
+        t = [x.clone().requires_grad_(True) for x in (xyz, op, sh, sc, rot)]
+        m2d = torch.zeros(V, P, 3, device=DEV, requires_grad=True)
+        c, r, d, a = R.rasterize_views(means3D=t[0], opacities=t[1], viewmatrices=vm, projmatrices=pm, camposs=cp, tanfovx=tanx,
+                                       tanfovy=tany, image_height=HW, image_width=HW, bg=bg, sh_degree=0, shs=t[2], scales=t[3],
+                                       rotations=t[4], means2D=m2d)
+        ((c * gw).sum() + d.sum() + a.sum()).backward()
+        return (c, r, d, a), [x.grad for x in t] + [m2d.grad]
+
+    full, g_full = run()
+    total = R.last_num_rendered()
+    assert total == P * V * 64
+    monkeypatch.setattr(R, "MAX_INSTANCES", total // 3)  # forces two levels of halving: 8 -> 4 -> 2 views per call
+    split, g_split = run()
+    assert R.last_num_rendered() == total // 4
+    for x, y in zip(full, split):
+        assert torch.equal(x, y)
+    for x, y in zip(g_full, g_split):
+        assert torch.allclose(x, y, rtol=1e-4, atol=1e-6)
