@@ -7,7 +7,7 @@
 #include "common.cuh"
 #include "kernels.h"
 
-__global__ void __launch_bounds__(256) reattach_kernel(int P, int n_frames, int n_verts, const float *__restrict__ vertices,
+__global__ void __launch_bounds__(256) reattach_kernel(int P, int n_frames, int n_verts, int n_faces, const float *__restrict__ vertices,
                                                         const int32_t *__restrict__ faces, const int32_t *__restrict__ map_face,
                                                         const float *__restrict__ map_uvw, const float *__restrict__ map_dist,
                                                         float *__restrict__ xyz)
@@ -16,7 +16,15 @@ __global__ void __launch_bounds__(256) reattach_kernel(int P, int n_frames, int 
     const int f = blockIdx.y;
     if (i >= P) return;
     const int fc = map_face[i];
+    float *o = xyz + ((size_t)f * P + i) * 3;
+    // an index outside the mesh never reads out of bounds: the Gaussian gets NaN positions (it is then culled by the
+    // preprocess and visible to the caller), where the reference's numpy indexing would raise IndexError
+    if ((unsigned)fc >= (unsigned)n_faces) { o[0] = o[1] = o[2] = __int_as_float(0x7fc00000); return; }
     const int i0 = faces[3 * fc], i1 = faces[3 * fc + 1], i2 = faces[3 * fc + 2];
+    if ((unsigned)i0 >= (unsigned)n_verts || (unsigned)i1 >= (unsigned)n_verts || (unsigned)i2 >= (unsigned)n_verts) {
+        o[0] = o[1] = o[2] = __int_as_float(0x7fc00000);
+        return;
+    }
     const float *vb = vertices + (size_t)f * n_verts * 3;
     const float a0 = vb[3 * i0], a1 = vb[3 * i0 + 1], a2 = vb[3 * i0 + 2];
     const float b0 = vb[3 * i1], b1 = vb[3 * i1 + 1], b2 = vb[3 * i1 + 2];
@@ -26,17 +34,16 @@ __global__ void __launch_bounds__(256) reattach_kernel(int P, int n_frames, int 
     const float inv = 1.0f / (sqrtf(n0 * n0 + n1 * n1 + n2 * n2) + 1e-20f);
     n0 *= inv; n1 *= inv; n2 *= inv;
     const float u = map_uvw[3 * i], v = map_uvw[3 * i + 1], w = map_uvw[3 * i + 2], d = map_dist[i];
-    float *o = xyz + ((size_t)f * P + i) * 3;
     o[0] = a0 * u + b0 * v + c0 * w + d * n0;
     o[1] = a1 * u + b1 * v + c1 * w + d * n1;
     o[2] = a2 * u + b2 * v + c2 * w + d * n2;
 }
 
-void launch_reattach(int P, int n_frames, int n_verts, const float *vertices, const int32_t *faces, const int32_t *map_face,
+void launch_reattach(int P, int n_frames, int n_verts, int n_faces, const float *vertices, const int32_t *faces, const int32_t *map_face,
                      const float *map_uvw, const float *map_dist, float *xyz, cudaStream_t st)
 {
     dim3 grid((P + 255) / 256, n_frames);
-    reattach_kernel<<<grid, 256, 0, st>>>(P, n_frames, n_verts, vertices, faces, map_face, map_uvw, map_dist, xyz);
+    reattach_kernel<<<grid, 256, 0, st>>>(P, n_frames, n_verts, n_faces, vertices, faces, map_face, map_uvw, map_dist, xyz);
 }
 
 __global__ void __launch_bounds__(256) pack_u8_kernel(const float *__restrict__ color, uint8_t *__restrict__ out, int64_t HW, int n_frames)

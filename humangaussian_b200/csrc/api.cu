@@ -300,7 +300,7 @@ int b200gs_reattach(int32_t P, int32_t n_frames, int32_t n_verts, int32_t n_face
         return B200GS_E_ARGS;
     if (n_frames > 65535) return B200GS_E_RANGE;
     if (P == 0) return B200GS_OK;
-    launch_reattach(P, n_frames, n_verts, vertices, faces, mapping_face, mapping_uvw, mapping_dist, xyz_out, (cudaStream_t)stream);
+    launch_reattach(P, n_frames, n_verts, n_faces, vertices, faces, mapping_face, mapping_uvw, mapping_dist, xyz_out, (cudaStream_t)stream);
     g_launches += 1;
     CK(cudaGetLastError(), "reattach launch");
     return B200GS_OK;
@@ -316,12 +316,12 @@ int b200gs_pack_frames_u8(const float *color, uint8_t *out, int32_t image_height
     return B200GS_OK;
 }
 
-int b200gs_densify_stats(int32_t P, int32_t n_views, const float *dL_dmeans2D, const int32_t *radii, float *xyz_gradient_accum,
-                         float *denom, float *max_radii2D, void *stream)
+int b200gs_densify_stats(int32_t P, int32_t n_views, const float *dL_dmeans2D, const int32_t *radii, const uint8_t *update_mask,
+                         float *xyz_gradient_accum, float *denom, float *max_radii2D, void *stream)
 {
     if (P < 0 || n_views < 1 || !dL_dmeans2D || !radii || !xyz_gradient_accum || !denom || !max_radii2D) return B200GS_E_ARGS;
     if (P == 0) return B200GS_OK;
-    launch_densify_stats(P, n_views, dL_dmeans2D, radii, xyz_gradient_accum, denom, max_radii2D, (cudaStream_t)stream);
+    launch_densify_stats(P, n_views, dL_dmeans2D, radii, update_mask, xyz_gradient_accum, denom, max_radii2D, (cudaStream_t)stream);
     g_launches += 1;
     CK(cudaGetLastError(), "densify_stats launch");
     return B200GS_OK;

@@ -161,8 +161,8 @@ __global__ void __launch_bounds__(DB) densify_plan_kernel(DensifyCfg c, int P, c
 }
 
 __global__ void __launch_bounds__(DB) densify_stats_kernel(int P, int V, const float *__restrict__ grads /*[V,P,3]*/,
-                                                           const int32_t *__restrict__ radii /*[V,P]*/, float *accum, float *denom,
-                                                           float *max_radii2D)
+                                                           const int32_t *__restrict__ radii /*[V,P]*/, const uint8_t *__restrict__ update_mask /*[P] or null*/,
+                                                           float *accum, float *denom, float *max_radii2D)
 {
     const int i = blockIdx.x * DB + threadIdx.x;
     if (i >= P) return;
@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(DB) densify_stats_kernel(int P, int V, const f
         gy = __fadd_rn(gy, g[1]);
         rmax = max(rmax, radii[(size_t)v * P + i]);
     }
-    if (rmax > 0) {
+    // visibility_filter = (max radius > 0) [& ~hand_mask when disable_hand_densification is set, GaussianDreamer.py:288-297]
+    if (rmax > 0 && (!update_mask || update_mask[i])) {
         max_radii2D[i] = fmaxf(max_radii2D[i], (float)rmax);
         accum[i] = __fadd_rn(accum[i], __fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy))));
         denom[i] = __fadd_rn(denom[i], 1.0f);
@@ -225,10 +226,10 @@ __global__ void __launch_bounds__(DB) densify_move_kernel(int P, int rf, const i
 
 size_t densify_scratch_bytes(int P) { return (size_t)4 * ((P + DB - 1) / DB + 1) * sizeof(int); }
 
-void launch_densify_stats(int P, int V, const float *grads, const int32_t *radii, float *accum, float *denom, float *max_radii2D,
-                          cudaStream_t st)
+void launch_densify_stats(int P, int V, const float *grads, const int32_t *radii, const uint8_t *update_mask, float *accum, float *denom,
+                          float *max_radii2D, cudaStream_t st)
 {
-    densify_stats_kernel<<<(P + DB - 1) / DB, DB, 0, st>>>(P, V, grads, radii, accum, denom, max_radii2D);
+    densify_stats_kernel<<<(P + DB - 1) / DB, DB, 0, st>>>(P, V, grads, radii, update_mask, accum, denom, max_radii2D);
 }
 
 void launch_densify_plan(const DensifyCfg &c, int P, const float *accum, const float *denom, const float *opacity, const float *scaling,

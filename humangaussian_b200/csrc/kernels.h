@@ -89,7 +89,7 @@ int blend_sgrad_is_moments(); // which ScreenGrad format the linked blend_bwd wr
 void launch_test_exp(const float *x, float *y, int64_t n, cudaStream_t st);
 
 // animation frame path (anim.cu)
-void launch_reattach(int P, int n_frames, int n_verts, const float *vertices, const int32_t *faces, const int32_t *map_face,
+void launch_reattach(int P, int n_frames, int n_verts, int n_faces, const float *vertices, const int32_t *faces, const int32_t *map_face,
                      const float *map_uvw, const float *map_dist, float *xyz, cudaStream_t st);
 void launch_pack_u8(const float *color, uint8_t *out, int H, int W, int n_frames, cudaStream_t st);
 
@@ -108,8 +108,8 @@ struct DensifyCfg {
     float big_ws_thresh; // 0.1 * extent (mode 0) or size_thresh (mode 1)
 };
 size_t densify_scratch_bytes(int P);
-void launch_densify_stats(int P, int V, const float *grads, const int32_t *radii, float *accum, float *denom, float *max_radii2D,
-                          cudaStream_t st);
+void launch_densify_stats(int P, int V, const float *grads, const int32_t *radii, const uint8_t *update_mask, float *accum, float *denom,
+                          float *max_radii2D, cudaStream_t st);
 void launch_densify_plan(const DensifyCfg &c, int P, const float *accum, const float *denom, const float *opacity, const float *scaling,
                          int *plan, int *counts, char *scratch, cudaStream_t st);
 void launch_densify_move(int role, int P, int rf, const int *plan, const float *src, float *dst, int n_split, int S_sel, int S_kept,

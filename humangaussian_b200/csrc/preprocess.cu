@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256, PFWD_MIN_BLOCKS) preprocess_fwd_kernel(Pr
         const float ty = gs_affine(V[1], V[5], V[9], V[13], px, py, pz);
         const float tz = gs_affine(V[2], V[6], V[10], V[14], px, py, pz);
         do {
-            if (tz <= GS_NEAR_Z) break;
+            if (!(tz > GS_NEAR_Z)) break; // near-plane cull (A.2 step 1); written so that a NaN position is culled too
             const float hx = gs_affine(PV[0], PV[4], PV[8], PV[12], px, py, pz);
             const float hy = gs_affine(PV[1], PV[5], PV[9], PV[13], px, py, pz);
             const float hw = gs_affine(PV[3], PV[7], PV[11], PV[15], px, py, pz);

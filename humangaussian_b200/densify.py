@@ -55,11 +55,14 @@ def _need_cuda(t: torch.Tensor):
         raise RuntimeError("b200gs: tensors must live on a CUDA device (there is no CPU path)")
 
 
-def add_densification_stats(stats: DensifyStats, viewspace_grads: torch.Tensor, radii: torch.Tensor) -> None:
+def add_densification_stats(stats: DensifyStats, viewspace_grads: torch.Tensor, radii: torch.Tensor,
+                            update_mask: Optional[torch.Tensor] = None) -> None:
     """One optimiser step of bookkeeping for a batch of views, in place.
     viewspace_grads [V,P,3] (or [P,3]): the means2D gradients of the step's views; radii [V,P] (or [P]) int32.
     Equals GaussianDreamer.py:385-391: sum the view gradients, visibility = max radius > 0, max_radii2D update,
-    then GaussianModel.add_densification_stats (gaussian_model.py:433-437)."""
+    then GaussianModel.add_densification_stats (gaussian_model.py:433-437).
+    update_mask [P] bool/uint8 (optional) is ANDed with the visibility: the reference removes near-hand points from
+    visibility_filter before this bookkeeping when disable_hand_densification is set (GaussianDreamer.py:288-297)."""
     L = load_library()
     g = viewspace_grads.detach()
     if g.dim() == 2:
@@ -74,8 +77,13 @@ def add_densification_stats(stats: DensifyStats, viewspace_grads: torch.Tensor, 
     for t in (stats.xyz_gradient_accum, stats.denom, stats.max_radii2D):
         if not (t.is_contiguous() and t.dtype == torch.float32 and t.device == g.device):
             raise ValueError("b200gs: statistics must be contiguous fp32 tensors on the gradients' device")
+    m = None
+    if update_mask is not None:
+        m = update_mask.to(device=g.device, dtype=torch.uint8).contiguous()
+        if m.shape != (P,):
+            raise ValueError("b200gs: update_mask must have shape [P]")
     with torch.cuda.device(g.device):
-        _check(L.b200gs_densify_stats(P, V, _ptr(g), _ptr(r), _ptr(stats.xyz_gradient_accum), _ptr(stats.denom),
+        _check(L.b200gs_densify_stats(P, V, _ptr(g), _ptr(r), _ptr(m), _ptr(stats.xyz_gradient_accum), _ptr(stats.denom),
                                       _ptr(stats.max_radii2D), _stream(g.device)), "densify_stats")
 
 

@@ -105,7 +105,7 @@ def load_library():
     L.b200gs_dist2_knn3.restype = C.c_int
     L.b200gs_dist2_knn3.argtypes = [i32, vp, vp, vp, sz, vp]
     L.b200gs_densify_stats.restype = C.c_int
-    L.b200gs_densify_stats.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
+    L.b200gs_densify_stats.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.b200gs_densify_scratch_bytes.restype = sz; L.b200gs_densify_scratch_bytes.argtypes = [i32]
     L.b200gs_densify_plan.restype = C.c_int
     L.b200gs_densify_plan.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]

@@ -126,7 +126,9 @@ int b200gs_mark_visible(int32_t P, const float *positions, const float *viewmatr
  * Re-attachment of the Gaussians to a re-posed body mesh, for n_frames poses at once (animation.py:383-403 does one
  * frame per call in numpy): xyz_out[f,i] = u*v0 + v*v1 + w*v2 + dist[i] * unit_normal(face), face = faces[mapping_face[i]].
  *   vertices [n_frames, n_verts, 3]; faces [n_faces,3] int32; mapping_face [P] int32; mapping_uvw [P,3]; mapping_dist [P];
- *   xyz_out [n_frames, P, 3] -- feed it to b200gs_forward with means3D_per_view = 1. */
+ *   xyz_out [n_frames, P, 3] -- feed it to b200gs_forward with means3D_per_view = 1.
+ *   A mapping_face outside [0, n_faces) or a face index outside [0, n_verts) is never dereferenced: that Gaussian's
+ *   positions become NaN (it is culled by the preprocess), where the reference's numpy indexing raises. */
 int b200gs_reattach(int32_t P, int32_t n_frames, int32_t n_verts, int32_t n_faces, const float *vertices, const int32_t *faces,
                     const int32_t *mapping_face, const float *mapping_uvw, const float *mapping_dist, float *xyz_out, void *stream);
 /* clamp(color,0,1) (gs_renderer.py:1017) then CHW float -> HWC uint8 by truncation of x*255 (animation.py:1011).
@@ -147,8 +149,10 @@ int b200gs_dist2_knn3(int32_t P, const float *points, float *mean_dist2, void *s
  * b200gs_densify_stats: one optimiser step's bookkeeping for a V-view batch (GaussianDreamer.py:385-391 +
  *   add_densification_stats, gaussian_model.py:433-437): g = sum_v dL_dmeans2D[v] ; r = max_v radii[v] ; where r > 0:
  *   max_radii2D = max(max_radii2D, r), xyz_gradient_accum += |g.xy|, denom += 1.
- *     dL_dmeans2D [V,P,3] (what b200gs_backward wrote), radii [V,P] int32; accum, denom, max_radii2D [P] (in/out). */
-int b200gs_densify_stats(int32_t P, int32_t n_views, const float *dL_dmeans2D, const int32_t *radii,
+ *     dL_dmeans2D [V,P,3] (what b200gs_backward wrote), radii [V,P] int32; accum, denom, max_radii2D [P] (in/out).
+ *   update_mask [P] uint8 or NULL: ANDed with r > 0 -- the reference's visibility_filter can exclude points before this
+ *   bookkeeping (disable_hand_densification / hand_radius, GaussianDreamer.py:288-297). */
+int b200gs_densify_stats(int32_t P, int32_t n_views, const float *dL_dmeans2D, const int32_t *radii, const uint8_t *update_mask,
                          float *xyz_gradient_accum, float *denom, float *max_radii2D, void *stream);
 
 typedef struct b200gs_densify_cfg {

@@ -108,3 +108,22 @@ def test_render_frames_end_to_end():
     frames = render_frames(p, xyz, cams, torch.zeros(3, device=DEV))
     assert frames.shape == (F, 128, 128, 3) and frames.dtype == torch.uint8
     assert int(frames.max()) > 50 and not torch.equal(frames[0], frames[35])
+
+
+def test_reattach_out_of_range_indices_are_not_dereferenced():
+    """A mapping_face / face index outside the mesh gives NaN positions (culled downstream), never an out-of-bounds read."""
+    from humangaussian_b200.animation import reattach
+    rng = np.random.RandomState(0)
+    Nv, Nf, P = 50, 80, 1000
+    verts = rng.randn(2, Nv, 3).astype(np.float32)
+    faces = np.stack([rng.permutation(Nv)[:3] for _ in range(Nf)]).astype(np.int32)
+    faces[7, 1] = Nv + 1000000                       # a corrupt face
+    mface = rng.randint(0, Nf, P).astype(np.int32)
+    mface[:5] = [-1, Nf, Nf + 12345678, 7, 3]
+    uvw = rng.dirichlet([1, 1, 1], P).astype(np.float32)
+    dist = np.zeros(P, np.float32)
+    got = reattach(torch.tensor(verts, device=DEV), torch.tensor(faces), torch.tensor(mface), torch.tensor(uvw), torch.tensor(dist))
+    torch.cuda.synchronize()
+    bad = (mface < 0) | (mface >= Nf) | (mface == 7)
+    g = got.cpu().numpy()
+    assert np.isnan(g[:, bad]).all() and np.isfinite(g[:, ~bad]).all()
