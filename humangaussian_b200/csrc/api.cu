@@ -115,6 +115,7 @@ int b200gs_forward(const b200gs_params *prm, const float *means3D, const float *
         PreArgs a;
         a.P = P; a.deg = shs ? prm->sh_degree : 0; a.M = prm->sh_coeffs; a.H = H; a.W = W; a.grid_x = gx; a.grid_y = gy;
         a.vec16 = ((((uintptr_t)rotations) | ((uintptr_t)shs)) & 15) == 0; // any 4-byte-aligned float pointer is accepted
+        a.raw = prm->raw_params != 0;
         a.mod = prm->scale_modifier;
         a.means_view_stride = prm->means3D_per_view ? (size_t)3 * P : 0;
         a.means = means3D; a.shs = shs; a.colors_pre = colors_precomp; a.opac = opacities; a.scales = scales;
@@ -173,9 +174,10 @@ int b200gs_backward(const b200gs_params *prm, const float *means3D, const float 
                     float *dL_dopacity, float *dL_dscales, float *dL_drots, float *dL_dcov3D, void *scratch,
                     size_t scratch_bytes, void *stream)
 {
-    (void)opacities; (void)num_rendered;
+    (void)num_rendered;
     int rc = check_common(prm, shs, colors_precomp, scales, rotations, cov3D_precomp);
     if (rc) return rc;
+    if (prm->raw_params && !opacities) return B200GS_E_ARGS;
     if (!means3D || !bg || !viewmatrix || !projmatrix || !campos || !radii || !geom_buf || !binning_buf || !image_buf ||
         !dL_dmeans3D || !dL_dmeans2D || !dL_dopacity || !scratch)
         return B200GS_E_ARGS;
@@ -206,6 +208,7 @@ int b200gs_backward(const b200gs_params *prm, const float *means3D, const float 
     PreBwdArgs a;
     a.P = P; a.V = V; a.deg = shs ? prm->sh_degree : 0; a.M = prm->sh_coeffs; a.H = H; a.W = W; a.mod = prm->scale_modifier;
     a.vec16 = (((uintptr_t)dL_drots) & 15) == 0;
+    a.raw = prm->raw_params != 0; a.opac = opacities;
     a.means_view_stride = prm->means3D_per_view ? (size_t)3 * P : 0;
     a.means = means3D; a.shs = shs; a.colors_pre = colors_precomp; a.scales = scales; a.rots = rotations; a.cov_pre = cov3D_precomp;
     a.view = viewmatrix; a.proj = projmatrix; a.campos = campos;

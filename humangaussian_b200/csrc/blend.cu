@@ -24,10 +24,20 @@
 #ifndef WARPS_PER_CTA
 #define WARPS_PER_CTA 2 // independent patches per CTA (1, 2, 4 or 8); swept on B200: 2 is best by ~2 %
 #endif
+#ifndef BWD_MMA
+#define BWD_MMA 1 // 1: per-Gaussian sums over the patch as a tensor-core contraction; 0: the 12-shuffle butterfly
+#endif
 #ifndef BWD_MIN_BLOCKS
+#if BWD_MMA
+#define BWD_MIN_BLOCKS 14 // 14.5 KB of staging per CTA: 14 CTAs (28 warps) fill the SM's shared memory; 72 registers
+#else
 #define BWD_MIN_BLOCKS 16 // caps the backward kernel at 64 registers (32 warps/SM); 18 / 20 blocks (55 / 48 regs) measured slower
 #endif
+#endif
 #define CTAS_PER_TILE (8 / WARPS_PER_CTA)
+#ifndef CULL_EXACT
+#define CULL_EXACT 1 // second cull stage: exact ellipse-vs-patch test on the hits of the support-box test
+#endif
 
 // does the support box [px-hx,px+hx] x [py-hy,py+hy] reach the patch [x0,x0+7] x [y0,y0+3] ?
 __device__ __forceinline__ bool box_hits_patch(const float4 g0, float x0, float y0)
@@ -60,7 +70,11 @@ __device__ __forceinline__ bool ellipse_hits_patch(const float4 g0, const float4
 #ifdef BLEND_COUNTERS
 // instrumentation build only (tests/gpu_r2_probe.py): visit statistics of the patch walk
 __device__ unsigned long long g_blend_cnt[16];
-#define CNT_ADD(i, v) do { if (lane == 0) atomicAdd(&g_blend_cnt[i], (unsigned long long)(v)); } while (0)
+// per-warp register accumulators, ONE atomic per counter per warp at kernel end (per-visit atomics on 16 addresses serialise
+// the whole grid: measured the hard way)
+#define CNT_DECL unsigned cnt_loc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define CNT_ADD(i, v) do { cnt_loc[(i) & 7] += (unsigned)(v); } while (0)
+#define CNT_FLUSH(o) do { if (lane == 0) for (int c_ = 0; c_ < 8; c_++) if (cnt_loc[c_]) atomicAdd(&g_blend_cnt[(o) + c_], (unsigned long long)cnt_loc[c_]); } while (0)
 extern "C" int b200gs_debug_counters(unsigned long long *out, int reset)
 {
     cudaMemcpyFromSymbol(out, g_blend_cnt, sizeof(g_blend_cnt));
@@ -68,7 +82,9 @@ extern "C" int b200gs_debug_counters(unsigned long long *out, int reset)
     return 0;
 }
 #else
+#define CNT_DECL
 #define CNT_ADD(i, v) do { } while (0)
+#define CNT_FLUSH(o) do { } while (0)
 #endif
 
 // power with the conic pre-scaled at staging time (A' = -A/2, B' = -B, C' = -C/2: exact operations, so the
@@ -82,9 +98,7 @@ __device__ __forceinline__ float power_prescaled(float Ap, float Bp, float Cp, f
 
 // per-warp slab of the (at most 32) hits of the current chunk
 struct __align__(16) WarpSlab {
-    float4 rec[32 * 3]; // px,py,hx,hy | A',B',C',o | r,g,b,depth
-    uint32_t pos[32];   // 1-based position in the tile list (forward) / 0-based (backward)
-    uint32_t id[32];    // record index (backward: address of the ScreenGrad accumulator)
+    float4 rec[32 * 3]; // px,py,list position,record index | A',B',C',o | r,g,b,depth
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -116,6 +130,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_fwd_kernel(BlendArgs
 
     // T == 0 is the "done" sentinel: a finished (or out-of-image) pixel keeps failing the T test and never
     // accumulates, exactly like upstream's `done` flag; T_out remembers the transmittance to report.
+    CNT_DECL;
     float T = inside ? 1.0f : 0.0f, T_out = 1.0f;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, Dd = 0.f, Aa = 0.f;
     uint32_t last = 0;
@@ -129,29 +144,31 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_fwd_kernel(BlendArgs
     if (lane < n_total) g0_c = __ldg(recs4 + 3 * (size_t)id_c);
     for (int base = 0; base < n_total; base += 32) {
         if (__all_sync(FULL, T == 0.0f)) break;
-        const bool hit = box_hits_patch(g0_c, fx0, fy0);
-        const uint32_t b = __ballot_sync(FULL, hit);
+        bool hit = box_hits_patch(g0_c, fx0, fy0);
         float4 g1, g2;
-        if (hit) {
-            g1 = __ldg(recs4 + 3 * (size_t)id_c + 1);
-            g2 = __ldg(recs4 + 3 * (size_t)id_c + 2);
-        }
+        if (hit) g1 = __ldg(recs4 + 3 * (size_t)id_c + 1);
         const float4 g0_h = g0_c;
+        const uint32_t id_h = id_c;
         id_c = id_n;
         g0_c = make_float4(0.f, 0.f, -1.f, -1.f);
         if (base + 32 + lane < n_total) g0_c = __ldg(recs4 + 3 * (size_t)id_c);
         if (base + 64 + lane < n_total) id_n = __ldg(plist + base + 64 + lane);
 #ifdef BLEND_COUNTERS
-        CNT_ADD(0, 1); CNT_ADD(1, min(32, n_total - base)); CNT_ADD(2, __popc(b));
-        CNT_ADD(3, __popc(__ballot_sync(FULL, hit && ellipse_hits_patch(g0_h, g1, fx0, fy0))));
+        CNT_ADD(0, 1); CNT_ADD(1, min(32, n_total - base)); CNT_ADD(2, __popc(__ballot_sync(FULL, hit)));
 #endif
+#if CULL_EXACT
+        if (hit) hit = ellipse_hits_patch(g0_h, g1, fx0, fy0);
+#endif
+        const uint32_t b = __ballot_sync(FULL, hit);
+        if (hit) g2 = __ldg(recs4 + 3 * (size_t)id_h + 2);
+        CNT_ADD(3, __popc(b));
         if (b == 0u) continue;
         if (hit) {
             const int slot = __popc(b & lt);
-            sl.rec[3 * slot] = g0_h;
+            // (px, py, 1-based list position, -) : the support box has done its job, its two words carry bookkeeping
+            sl.rec[3 * slot] = make_float4(g0_h.x, g0_h.y, __uint_as_float((uint32_t)(base + lane + 1)), 0.f);
             sl.rec[3 * slot + 1] = make_float4(fmul(-0.5f, g1.x), -g1.y, fmul(-0.5f, g1.z), g1.w);
             sl.rec[3 * slot + 2] = g2;
-            sl.pos[slot] = (uint32_t)(base + lane + 1);
         }
         __syncwarp();
         const int cnt = __popc(b);
@@ -180,13 +197,14 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_fwd_kernel(BlendArgs
                         Dd = ffma(q2.w, w, Dd);
                         Aa = fadd(Aa, w);
                         T = test_T;
-                        last = sl.pos[i];
+                        last = __float_as_uint(g0.z);
                     }
                 }
             }
         }
         __syncwarp();
     }
+    CNT_FLUSH(0);
     if (inside) {
         if (T != 0.0f) T_out = T;
         const size_t HW = (size_t)a.H * a.W;
@@ -243,9 +261,115 @@ __device__ __forceinline__ int slot_of_lane(int lane)
     return (h16 ? 5 : 0) + (h8 ? 3 : 0) + (h4 ? 2 : 0) + (h2 ? 1 : 0);
 }
 
+#if BWD_MMA
+// ---- B1, contraction form ---------------------------------------------------------------------------------------------
+// The ten per-(warp, Gaussian) sums are two small matrix products over the 32 pixels of the patch:
+//     M[hit, f] = sum_pix q[hit, pix] * Phi[pix, f]      Phi = (1, x, y, x^2, x*y, y^2), x,y = pixel offset inside the patch
+//     C[hit, c] = sum_pix w[hit, pix] * G[pix, c]        G   = the pixel's upstream gradient (gC0, gC1, gC2, gD)
+// Phi and G do not depend on the Gaussian, so both are B operands that stay put while q and w of 16 hits are staged in a
+// per-warp shared-memory tile (row = hit, column = pixel lane) and read back as the A fragments of mma.sync.m16n8k8 (TF32
+// inputs, FP32 accumulate).  Precision: every FP32 operand is split into two TF32 halves (hi = rna(x), lo = rna(x - hi):
+// 22+ significant bits); Phi's entries are integers <= 49, exact in TF32; for G the three products hi*hi + lo*hi + hi*lo
+// are kept (the dropped lo*lo term is 2^-24 relative).  The patch-local moments are shifted to the Gaussian's centre
+// (dx = cx - x, cx = px - x0) by the three lanes of a quad that hold them, then leave as 8-byte vector reductions.
+// Per 16 hits: 20 HMMA + ~150 staging/epilogue instructions instead of 16 x (46-instruction butterfly + 9 products + RED).
+#define QS_STRIDE 36 // floats per staged row: 36 = 4 (mod 32) makes the A-fragment reads (row = lane/4, col = lane%4) conflict-free
+struct __align__(16) BwdStage {
+    float q[16 * QS_STRIDE];
+    float w[16 * QS_STRIDE];
+    float4 info[16]; // per staged hit: cx = px - x0, cy = py - y0, record index (bits), -
+    float ghi[32 * 4], glo[32 * 4]; // per pixel lane: TF32 halves of (gC0, gC1, gC2, gD)
+};
+
+__device__ __forceinline__ uint32_t tf32_rna(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void tf32_split(float x, uint32_t &hi, uint32_t &lo)
+{
+    hi = tf32_rna(x);
+    lo = tf32_rna(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void red_add_v2(float *addr, float x, float y)
+{
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(x), "f"(y) : "memory");
+}
+
+// reduce the nb (<= 16) staged hits of this warp and add them to their ScreenGrad records
+__device__ __forceinline__ void bwd_flush(BwdStage &sg, const uint32_t (&phb)[8], float *sgrad, int nb, int lane)
+{
+    const int gid = lane >> 2, tig = lane & 3;
+    __syncwarp();
+    float c[4] = {0.f, 0.f, 0.f, 0.f}, d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; j++) { // k-step j = the patch's pixel row j (8 pixels)
+        uint32_t hi[4], lo[4];
+        const float *qa = sg.q + gid * QS_STRIDE + 8 * j + tig;
+        tf32_split(qa[0], hi[0], lo[0]);
+        tf32_split(qa[8 * QS_STRIDE], hi[1], lo[1]);
+        tf32_split(qa[4], hi[2], lo[2]);
+        tf32_split(qa[8 * QS_STRIDE + 4], hi[3], lo[3]);
+        mma_tf32(c, hi, phb[2 * j], phb[2 * j + 1]);
+        mma_tf32(c, lo, phb[2 * j], phb[2 * j + 1]);
+        const float *wa = sg.w + gid * QS_STRIDE + 8 * j + tig;
+        tf32_split(wa[0], hi[0], lo[0]);
+        tf32_split(wa[8 * QS_STRIDE], hi[1], lo[1]);
+        tf32_split(wa[4], hi[2], lo[2]);
+        tf32_split(wa[8 * QS_STRIDE + 4], hi[3], lo[3]);
+        // B[k = pixel 8j + tig (+4)][n = gid] = G[pixel][gid] for gid < 4, else 0
+        const int gi = (8 * j + tig) * 4 + (gid & 3);
+        const bool gv = gid < 4;
+        const uint32_t gh0 = gv ? __float_as_uint(sg.ghi[gi]) : 0u, gh1 = gv ? __float_as_uint(sg.ghi[gi + 16]) : 0u;
+        const uint32_t gl0 = gv ? __float_as_uint(sg.glo[gi]) : 0u, gl1 = gv ? __float_as_uint(sg.glo[gi + 16]) : 0u;
+        mma_tf32(d, hi, gh0, gh1);
+        mma_tf32(d, lo, gh0, gh1);
+        mma_tf32(d, hi, gl0, gl1);
+    }
+    // c[0],c[1] = features 2*tig, 2*tig+1 of hit gid; c[2],c[3] = the same of hit gid+8   (features: S0 Sx | Sy Sxx | Sxy Syy | - -)
+    // d likewise                                                                          (gC0 gC1 | gC2 gD | - - | - -)
+    const int q0 = lane & ~3;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const float m0 = c[2 * r], m1 = c[2 * r + 1];
+        const float S0 = __shfl_sync(FULL, m0, q0), Sx = __shfl_sync(FULL, m1, q0), Sy = __shfl_sync(FULL, m0, q0 + 1);
+        const int row = gid + 8 * r;
+        if (row < nb && tig < 3) {
+            const float4 inf = sg.info[row];
+            const float cx = inf.x, cy = inf.y;
+            float o0, o1; // patch-local moments -> moments about the Gaussian's centre: dx = cx - x, dy = cy - y
+            if (tig == 0) {
+                o0 = m0;                                         // S0
+                o1 = cx * S0 - m1;                               // Sx'  = cx S0 - Sx
+            } else if (tig == 1) {
+                o0 = cy * S0 - m0;                               // Sy'  = cy S0 - Sy
+                o1 = cx * (cx * S0 - 2.0f * Sx) + m1;            // Sxx' = cx^2 S0 - 2 cx Sx + Sxx
+            } else {
+                o0 = cx * (cy * S0 - Sy) - cy * Sx + m0;         // Sxy' = cx cy S0 - cx Sy - cy Sx + Sxy
+                o1 = cy * (cy * S0 - 2.0f * Sy) + m1;            // Syy' = cy^2 S0 - 2 cy Sy + Syy
+            }
+            float *rec = sgrad + 12 * (size_t)__float_as_uint(inf.z);
+            red_add_v2(rec + 2 * tig, o0, o1);
+            if (tig < 2) red_add_v2(rec + 6 + 2 * tig, d[2 * r], d[2 * r + 1]);
+        }
+    }
+    __syncwarp();
+}
+#endif // BWD_MMA
+
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_kernel(BlendBwdArgs a)
 {
     __shared__ WarpSlab slabs[WARPS_PER_CTA];
+#if BWD_MMA
+    __shared__ BwdStage stages[WARPS_PER_CTA];
+#endif
 
     const int ntiles = a.grid_x * a.grid_y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -288,8 +412,34 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
     if (wmax == 0) return;
 
     const float bg_dot = a.bg[0] * gC0 + a.bg[1] * gC1 + a.bg[2] * gC2;
+#if BWD_MMA
+    BwdStage &sg = stages[warp];
+    {   // B operands: this lane's pixel gradient as TF32 halves (read back by pixel), and the constant pixel basis
+        uint32_t h, l;
+        tf32_split(gC0, h, l); sg.ghi[4 * lane + 0] = __uint_as_float(h); sg.glo[4 * lane + 0] = __uint_as_float(l);
+        tf32_split(gC1, h, l); sg.ghi[4 * lane + 1] = __uint_as_float(h); sg.glo[4 * lane + 1] = __uint_as_float(l);
+        tf32_split(gC2, h, l); sg.ghi[4 * lane + 2] = __uint_as_float(h); sg.glo[4 * lane + 2] = __uint_as_float(l);
+        tf32_split(gD, h, l);  sg.ghi[4 * lane + 3] = __uint_as_float(h); sg.glo[4 * lane + 3] = __uint_as_float(l);
+    }
+    uint32_t phb[8]; // Phi[pixel (x = tig + 4h, y = j)][feature gid], B fragment of k-step j: exact small integers
+    {
+        const int gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const float x = (float)(tig + 4 * h), y = (float)j;
+                const float f = gid == 0 ? 1.0f : gid == 1 ? x : gid == 2 ? y : gid == 3 ? x * x : gid == 4 ? x * y : gid == 5 ? y * y : 0.0f;
+                phb[2 * j + h] = __float_as_uint(f);
+            }
+    }
+    float *const sgrad_f = reinterpret_cast<float *>(a.sgrad);
+    int nb = 0; // hits staged and not yet reduced
+    __syncwarp();
+#else
     const int slot = slot_of_lane(lane);
     float *const sg_slot = reinterpret_cast<float *>(a.sgrad) + (slot >= 0 ? slot : 0); // this lane's column of ScreenGrad
+#endif
     // Per-pixel state of the back-to-front replay.  Upstream keeps five "accumulated colour behind" recurrences
     // (r,g,b,depth,alpha), each rec = last_alpha*last_c + (1-last_alpha)*rec, and forms sum_ch (c_ch - rec_ch)*g_ch.
     // The recurrences are linear with identical coefficients, so their dot product with the pixel's fixed upstream
@@ -300,6 +450,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
     const float Kbg = T_final * bg_dot;
     float rg = 0.f, last_cg = 0.f, last_alpha = 0.f;
 
+    CNT_DECL;
     // back to front: chunk [hi-32, hi), lane l <-> list position hi-1-l; the next chunk's loads are in flight
     uint32_t id_c = 0, id_n = 0;
     float4 g0_c = make_float4(0.f, 0.f, -1.f, -1.f);
@@ -307,13 +458,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
     if (wmax - 33 - lane >= 0) id_n = __ldg(plist + (wmax - 33 - lane));
     if (wmax - 1 - lane >= 0) g0_c = __ldg(recs4 + 3 * (size_t)id_c);
     for (int hi = wmax; hi > 0; hi -= 32) {
-        const bool hit = box_hits_patch(g0_c, fx0, fy0);
-        const uint32_t b = __ballot_sync(FULL, hit);
+        bool hit = box_hits_patch(g0_c, fx0, fy0);
         float4 g1, g2;
-        if (hit) {
-            g1 = __ldg(recs4 + 3 * (size_t)id_c + 1);
-            g2 = __ldg(recs4 + 3 * (size_t)id_c + 2);
-        }
+        if (hit) g1 = __ldg(recs4 + 3 * (size_t)id_c + 1);
         const float4 g0_h = g0_c;
         const uint32_t id_h = id_c;
         id_c = id_n;
@@ -321,23 +468,27 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
         if (hi - 33 - lane >= 0) g0_c = __ldg(recs4 + 3 * (size_t)id_c);
         if (hi - 65 - lane >= 0) id_n = __ldg(plist + (hi - 65 - lane));
 #ifdef BLEND_COUNTERS
-        CNT_ADD(8, 1); CNT_ADD(9, min(32, hi)); CNT_ADD(10, __popc(b));
-        CNT_ADD(11, __popc(__ballot_sync(FULL, hit && ellipse_hits_patch(g0_h, g1, fx0, fy0))));
+        CNT_ADD(8, 1); CNT_ADD(9, min(32, hi)); CNT_ADD(10, __popc(__ballot_sync(FULL, hit)));
 #endif
+#if CULL_EXACT
+        if (hit) hit = ellipse_hits_patch(g0_h, g1, fx0, fy0);
+#endif
+        const uint32_t b = __ballot_sync(FULL, hit);
+        if (hit) g2 = __ldg(recs4 + 3 * (size_t)id_h + 2);
+        CNT_ADD(11, __popc(b));
         if (b == 0u) continue;
         if (hit) {
             const int s = __popc(b & lt);
-            sl.rec[3 * s] = g0_h;
+            // (px, py, 0-based list position, record index)
+            sl.rec[3 * s] = make_float4(g0_h.x, g0_h.y, __uint_as_float((uint32_t)(hi - 1 - lane)), __uint_as_float(id_h));
             sl.rec[3 * s + 1] = make_float4(fmul(-0.5f, g1.x), -g1.y, fmul(-0.5f, g1.z), g1.w);
             sl.rec[3 * s + 2] = g2;
-            sl.pos[s] = (uint32_t)(hi - 1 - lane);
-            sl.id[s] = id_h;
         }
         __syncwarp();
         const int cnt = __popc(b);
         for (int i = 0; i < cnt; i++) {
-            const int pos = (int)sl.pos[i]; // 0-based position in the tile list
             const float4 g0 = sl.rec[3 * i], q1 = sl.rec[3 * i + 1];
+            const int pos = (int)__float_as_uint(g0.z); // 0-based position in the tile list
             const float dx = fsub(g0.x, fpx), dy = fsub(g0.y, fpy);
             const float power = power_prescaled(q1.x, q1.y, q1.z, dx, dy);
             const float G = gs_exp(power);
@@ -365,18 +516,40 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
                 const float dL_dalpha = fmaf(T, cg - rg, -(Kbg * inv));
                 q = G * dL_dalpha;
             }
+#if BWD_MMA
+            // stage this hit's q and w (row nb, column = pixel lane); sixteen staged hits are reduced at once
+            sg.q[nb * QS_STRIDE + lane] = q;
+            sg.w[nb * QS_STRIDE + lane] = w;
+            if (lane == 0) sg.info[nb] = make_float4(g0.x - fx0, g0.y - fy0, g0.w, 0.f);
+            if (++nb == 16) {
+                bwd_flush(sg, phb, sgrad_f, 16, lane);
+                nb = 0;
+            }
+#else
             // six moments of q over the patch: 1, dx, dy, dx^2, dx*dy, dy^2 (the conic / mean combination is linear
             // and happens once per Gaussian in B2)
             const float qx = q * dx, qy = q * dy;
             const float e = butterfly10(q, qx, qy, qx * dx, qx * dy, qy * dy, w * gC0, w * gC1, w * gC2, w * gD, lane);
-            if (slot >= 0) atomicAdd(sg_slot + 12 * (size_t)sl.id[i], e);
+            if (slot >= 0) atomicAdd(sg_slot + 12 * (size_t)__float_as_uint(g0.w), e);
+#endif
         }
         __syncwarp();
     }
+#if BWD_MMA
+    if (nb) bwd_flush(sg, phb, sgrad_f, nb, lane);
+#endif
+    CNT_FLUSH(8);
 }
 
 void launch_blend_bwd(const BlendBwdArgs &a, cudaStream_t st)
 {
+#if BWD_MMA
+    static bool once = false; // the staging tiles want the SM's full shared-memory carve-out (14 CTAs x 14.5 KB)
+    if (!once) {
+        cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        once = true;
+    }
+#endif
     const unsigned grid = (unsigned)(a.grid_x * a.grid_y * CTAS_PER_TILE * a.V);
     blend_bwd_kernel<<<grid, 32 * WARPS_PER_CTA, 0, st>>>(a);
 }

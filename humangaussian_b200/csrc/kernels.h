@@ -4,6 +4,7 @@
 
 struct PreArgs {
     int vec16;               // rotations and shs are 16-byte aligned: 128-bit loads allowed
+    int raw;                 // scales / rotations / opacities are the RAW parameters: exp / normalize / sigmoid applied here
     int P, deg, M, H, W, grid_x, grid_y;
     size_t means_view_stride; // 0: means shared by all views; 3*P: per-view positions
     float mod;
@@ -22,10 +23,11 @@ struct PreArgs {
 
 struct PreBwdArgs {
     int vec16;               // dL_drots is 16-byte aligned: 128-bit store allowed
+    int raw;                 // as PreArgs: gradients are then w.r.t. the raw parameters (activation Jacobians applied)
     int P, V, deg, M, H, W;
     size_t means_view_stride; // as PreArgs; when non-zero dL_dmeans3D is [V,P,3] (per view, not summed)
     float mod;
-    const float *means, *shs, *colors_pre, *scales, *rots, *cov_pre;
+    const float *means, *shs, *colors_pre, *scales, *rots, *cov_pre, *opac;
     const float *view, *proj, *campos;
     float tanfovx[GS_MAX_VIEWS], tanfovy[GS_MAX_VIEWS];
     const int32_t *radii;

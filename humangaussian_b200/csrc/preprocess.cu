@@ -75,6 +75,17 @@ __device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, flo
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(hi, max(lo, v)); }
 
+// torch.sigmoid / F.normalize(dim=1) as torch's CUDA kernels evaluate them in float32
+__device__ __forceinline__ float gs_sigmoid(float x) { return fdiv(1.0f, fadd(1.0f, expf(-x))); }
+__device__ __forceinline__ float gs_normalize4(float *q)
+{
+    const float n2 = fadd(fadd(fmul(q[0], q[0]), fmul(q[1], q[1])), fadd(fmul(q[2], q[2]), fmul(q[3], q[3])));
+    const float n = fmaxf(fsqrt(n2), 1e-12f);
+#pragma unroll
+    for (int k = 0; k < 4; k++) q[k] = fdiv(q[k], n);
+    return n;
+}
+
 // ------------------------------------------------------------------------------------------------
 // F1.  One thread per Gaussian; the thread loads its attributes ONCE (128-bit loads for the SH block when the
 // row pitch allows), builds the 3D covariance once, then loops over the V views of the batch writing one
@@ -92,14 +103,17 @@ __global__ void __launch_bounds__(256, PFWD_MIN_BLOCKS) preprocess_fwd_kernel(Pr
     if (i >= a.P) return;
 
     float px = __ldg(a.means + 3 * (size_t)i), py = __ldg(a.means + 3 * (size_t)i + 1), pz = __ldg(a.means + 3 * (size_t)i + 2);
-    const float op = __ldg(a.opac + i);
+    float op = __ldg(a.opac + i);
+    // raw parameters: the activations of GaussianModel's getters (gaussian_model.py:95-118) happen here,
+    // with the same float operations torch's CUDA kernels use (expf; 1/(1+expf(-x)); x / max(||x||, 1e-12))
+    if (a.raw) op = gs_sigmoid(op);
     float c6[6];
     if (a.cov_pre) {
 #pragma unroll
         for (int k = 0; k < 6; k++) c6[k] = __ldg(a.cov_pre + 6 * (size_t)i + k);
     } else {
-        const float s3[3] = {__ldg(a.scales + 3 * (size_t)i), __ldg(a.scales + 3 * (size_t)i + 1),
-                             __ldg(a.scales + 3 * (size_t)i + 2)};
+        float s3[3] = {__ldg(a.scales + 3 * (size_t)i), __ldg(a.scales + 3 * (size_t)i + 1),
+                       __ldg(a.scales + 3 * (size_t)i + 2)};
         float q[4];
         if (a.vec16) {
             const float4 q4 = __ldg(reinterpret_cast<const float4 *>(a.rots) + i);
@@ -107,6 +121,10 @@ __global__ void __launch_bounds__(256, PFWD_MIN_BLOCKS) preprocess_fwd_kernel(Pr
         } else {
 #pragma unroll
             for (int k = 0; k < 4; k++) q[k] = __ldg(a.rots + 4 * (size_t)i + k);
+        }
+        if (a.raw) {
+            s3[0] = expf(s3[0]); s3[1] = expf(s3[1]); s3[2] = expf(s3[2]);
+            gs_normalize4(q);
         }
         build_cov3d(s3, a.mod, q, c6);
     }
@@ -298,12 +316,16 @@ __global__ void __launch_bounds__(128, PBWD_MIN_BLOCKS) preprocess_bwd_kernel(Pr
     float px = a.means[3 * (size_t)i], py = a.means[3 * (size_t)i + 1], pz = a.means[3 * (size_t)i + 2];
 
     float c6[6];
-    float R[3][3], s[3] = {0, 0, 0}, q[4] = {0, 0, 0, 0};
+    float R[3][3], s[3] = {0, 0, 0}, q[4] = {0, 0, 0, 0}, qnorm = 1.0f;
     if (a.cov_pre) {
         for (int k = 0; k < 6; k++) c6[k] = a.cov_pre[6 * (size_t)i + k];
     } else {
-        const float s3[3] = {a.scales[3 * (size_t)i], a.scales[3 * (size_t)i + 1], a.scales[3 * (size_t)i + 2]};
+        float s3[3] = {a.scales[3 * (size_t)i], a.scales[3 * (size_t)i + 1], a.scales[3 * (size_t)i + 2]};
         for (int k = 0; k < 4; k++) q[k] = a.rots[4 * (size_t)i + k];
+        if (a.raw) { // the same activations F1 applied
+            s3[0] = expf(s3[0]); s3[1] = expf(s3[1]); s3[2] = expf(s3[2]);
+            qnorm = gs_normalize4(q);
+        }
         build_cov3d(s3, a.mod, q, c6);
         const float r = q[0], x = q[1], y = q[2], z = q[3];
         R[0][0] = 1.f - 2.f * (y * y + z * z); R[0][1] = 2.f * (x * y - r * z); R[0][2] = 2.f * (x * z + r * y);
@@ -477,6 +499,10 @@ __global__ void __launch_bounds__(128, PBWD_MIN_BLOCKS) preprocess_bwd_kernel(Pr
         float *o = a.dL_dmeans3D + 3 * ((a.means_view_stride ? (size_t)(a.V - 1) * a.P : 0) + (size_t)i);
         o[0] = dmean[0]; o[1] = dmean[1]; o[2] = dmean[2];
     }
+    if (a.raw) { // d sigmoid(x)/dx = o (1 - o)
+        const float o = gs_sigmoid(a.opac[i]);
+        dop *= o * (1.0f - o);
+    }
     a.dL_dopacity[i] = dop;
     if (DEG >= 0) {
         float *o = a.dL_dsh + (size_t)i * a.M * 3;
@@ -503,7 +529,8 @@ __global__ void __launch_bounds__(128, PBWD_MIN_BLOCKS) preprocess_bwd_kernel(Pr
             for (int k = 0; k < 3; k++) dLm[r2][k] = 2.f * (dS[r2][0] * L[0][k] + dS[r2][1] * L[1][k] + dS[r2][2] * L[2][k]);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            a.dL_dscales[3 * (size_t)i + k] = a.mod * (R[0][k] * dLm[0][k] + R[1][k] * dLm[1][k] + R[2][k] * dLm[2][k]);
+            // raw: d exp(x)/dx = exp(x) = s[k] / mod
+            a.dL_dscales[3 * (size_t)i + k] = (a.raw ? s[k] : a.mod) * (R[0][k] * dLm[0][k] + R[1][k] * dLm[1][k] + R[2][k] * dLm[2][k]);
 #pragma unroll
             for (int r2 = 0; r2 < 3; r2++) dR[r2][k] = dLm[r2][k] * s[k];
         }
@@ -513,6 +540,11 @@ __global__ void __launch_bounds__(128, PBWD_MIN_BLOCKS) preprocess_bwd_kernel(Pr
         dq.y = 2.f * y * (dR[0][1] + dR[1][0]) + 2.f * z * (dR[0][2] + dR[2][0]) + 2.f * r * (dR[2][1] - dR[1][2]) - 4.f * x * (dR[1][1] + dR[2][2]);
         dq.z = 2.f * x * (dR[0][1] + dR[1][0]) + 2.f * r * (dR[0][2] - dR[2][0]) + 2.f * z * (dR[1][2] + dR[2][1]) - 4.f * y * (dR[0][0] + dR[2][2]);
         dq.w = 2.f * r * (dR[1][0] - dR[0][1]) + 2.f * x * (dR[0][2] + dR[2][0]) + 2.f * y * (dR[1][2] + dR[2][1]) - 4.f * z * (dR[0][0] + dR[1][1]);
+        if (a.raw) { // Jacobian of x / max(||x||, eps): (dq - q_hat (q_hat . dq)) / ||x||   (F.normalize's autograd)
+            const float dot = r * dq.x + x * dq.y + y * dq.z + z * dq.w;
+            const float inv = 1.0f / qnorm;
+            dq.x = (dq.x - r * dot) * inv; dq.y = (dq.y - x * dot) * inv; dq.z = (dq.z - y * dot) * inv; dq.w = (dq.w - z * dot) * inv;
+        }
         if (a.vec16) reinterpret_cast<float4 *>(a.dL_drots)[i] = dq;
         else {
             float *o = a.dL_drots + 4 * (size_t)i;

@@ -28,7 +28,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # B200GS_LIB selects another build of the SAME C-ABI (only used to time baseline/libb200gs_classic.so, the
 # classic-structure comparator, through the identical host path).  It is not a fallback: the default is the product.
 LIB_PATH = os.environ.get("B200GS_LIB") or os.path.join(_HERE, "libb200gs.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_VIEWS = 64
 MAX_INSTANCES = 0x7FFFFFFF  # (Gaussian, tile) instances per call (B200GS_MAX_INSTANCES); larger batches are split by views
 
@@ -49,7 +49,8 @@ class _Params(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("P", C.c_int32), ("n_views", C.c_int32), ("sh_degree", C.c_int32),
                 ("sh_coeffs", C.c_int32), ("image_height", C.c_int32), ("image_width", C.c_int32),
                 ("prefiltered", C.c_int32), ("debug", C.c_int32), ("scale_modifier", C.c_float),
-                ("tanfovx", C.POINTER(C.c_float)), ("tanfovy", C.POINTER(C.c_float)), ("means3D_per_view", C.c_int32)]
+                ("tanfovx", C.POINTER(C.c_float)), ("tanfovy", C.POINTER(C.c_float)), ("means3D_per_view", C.c_int32),
+                ("raw_params", C.c_int32)]
 
 
 class _StateView(C.Structure):
@@ -232,17 +233,18 @@ class _Ctx:
                  "W", "M", "__weakref__")
 
 
-def _make_params(P, V, deg, M, H, W, mod, tanx, tany, prefiltered=False, debug=False, per_view_means=False):
+def _make_params(P, V, deg, M, H, W, mod, tanx, tany, prefiltered=False, debug=False, per_view_means=False, raw=False):
     tx = (C.c_float * V)(*[float(t) for t in tanx])
     ty = (C.c_float * V)(*[float(t) for t in tany])
     prm = _Params(ABI_VERSION, P, V, int(deg), int(M), int(H), int(W), int(bool(prefiltered)), int(bool(debug)), float(mod),
-                  C.cast(tx, C.POINTER(C.c_float)), C.cast(ty, C.POINTER(C.c_float)), int(bool(per_view_means)))
+                  C.cast(tx, C.POINTER(C.c_float)), C.cast(ty, C.POINTER(C.c_float)), int(bool(per_view_means)), int(bool(raw)))
     return prm, tx, ty
 
 
 def _forward_impl(means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, viewmatrix, projmatrix,
-                  campos, tanfovx, tanfovy, H, W, sh_degree, scale_modifier, prefiltered=False, debug=False):
-    """All tensors float32 contiguous on one CUDA device.  viewmatrix/projmatrix [V,4,4], campos [V,3]."""
+                  campos, tanfovx, tanfovy, H, W, sh_degree, scale_modifier, prefiltered=False, debug=False, raw=False):
+    """All tensors float32 contiguous on one CUDA device.  viewmatrix/projmatrix [V,4,4], campos [V,3].
+    raw: opacities / scales / rotations are GaussianModel's raw parameters (activations fused into the kernels)."""
     L = load_library()
     dev = means3D.device
     if dev.type != "cuda":
@@ -258,7 +260,7 @@ def _forward_impl(means3D, shs, colors_precomp, opacities, scales, rotations, co
             ((scales is not None or rotations is not None) and cov3D_precomp is not None):
         raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
     M = 0 if shs is None else shs.shape[1]
-    prm, tx, ty = _make_params(P, V, sh_degree, M, H, W, scale_modifier, tanfovx, tanfovy, prefiltered, debug, per_view_means)
+    prm, tx, ty = _make_params(P, V, sh_degree, M, H, W, scale_modifier, tanfovx, tanfovy, prefiltered, debug, per_view_means, raw)
     u8 = dict(dtype=torch.uint8, device=dev)
     color = torch.empty(V, 3, H, W, dtype=torch.float32, device=dev)
     depth = torch.empty(V, 1, H, W, dtype=torch.float32, device=dev)
@@ -348,11 +350,12 @@ class _RasterizeViews(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, cams, squeeze):
-        bg, viewmatrix, projmatrix, campos, tanx, tany, H, W, deg, mod, prefiltered, debug = cams
+        bg, viewmatrix, projmatrix, campos, tanx, tany, H, W, deg, mod, prefiltered, debug = cams[:12]
+        raw = bool(cams[12]) if len(cams) > 12 else False
         dev = means3D.device
         args = [_f32c(t, dev) for t in (means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp)]
         camt = [_f32c(t, dev) for t in (bg, viewmatrix, projmatrix, campos)]
-        color, radii, depth, alpha, st = _forward_impl(*args, *camt, tanx, tany, H, W, deg, mod, prefiltered, debug)
+        color, radii, depth, alpha, st = _forward_impl(*args, *camt, tanx, tany, H, W, deg, mod, prefiltered, debug, raw)
         ctx.st, ctx.squeeze = st, squeeze
         _save(ctx, args + camt)
         ctx.in_shapes = [None if t is None else t.shape for t in (means3D, means2D, shs, colors_precomp, opacities, scales,
@@ -432,8 +435,12 @@ class GaussianRasterizer(nn.Module):
 
 def rasterize_views(*, means3D, opacities, viewmatrices, projmatrices, camposs, tanfovx, tanfovy, image_height, image_width,
                     bg, sh_degree=0, shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None,
-                    means2D=None, scale_modifier=1.0):
+                    means2D=None, scale_modifier=1.0, raw=False):
     """Render V cameras of one Gaussian set in ONE call (one preprocess/sort/blend launch set, one host sync).
+
+    raw=True: `opacities`, `scales`, `rotations` are GaussianModel's RAW parameters (`_opacity`, `_scaling`, `_rotation`,
+    gaussian_model.py:44-59); sigmoid / exp / F.normalize run inside the preprocess kernel and their Jacobians inside the
+    backward kernel, so the returned gradients are w.r.t. the raw tensors and no activation kernels / autograd nodes exist.
 
     viewmatrices/projmatrices [V,4,4], camposs [V,3], tanfovx/tanfovy sequences of V floats.  means3D is [P,3]
     (shared: the SDS view batch) or [V,P,3] (per-view positions: the animation frame batch).  means2D, if given,
@@ -447,13 +454,13 @@ def rasterize_views(*, means3D, opacities, viewmatrices, projmatrices, camposs, 
                                 tanfovx=tanfovx[i:i + MAX_VIEWS], tanfovy=tanfovy[i:i + MAX_VIEWS], image_height=image_height,
                                 image_width=image_width, bg=bg, sh_degree=sh_degree, shs=shs, colors_precomp=colors_precomp,
                                 scales=scales, rotations=rotations, cov3D_precomp=cov3D_precomp,
-                                means2D=None if means2D is None else means2D[i:i + MAX_VIEWS], scale_modifier=scale_modifier)
+                                means2D=None if means2D is None else means2D[i:i + MAX_VIEWS], scale_modifier=scale_modifier, raw=raw)
                 for i in range(0, V, MAX_VIEWS)]
         return tuple(torch.cat([o[k] for o in outs], 0) for k in range(4))
     if means2D is None:
         means2D = torch.zeros(V, means3D.shape[-2], 3, dtype=torch.float32, device=means3D.device)
     cams = (bg, viewmatrices, projmatrices, camposs, list(tanfovx), list(tanfovy), int(image_height), int(image_width),
-            int(sh_degree), float(scale_modifier), False, False)
+            int(sh_degree), float(scale_modifier), False, False, bool(raw))
     try:
         return _RasterizeViews.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, cams, False)
     except InstanceLimitError:
@@ -465,7 +472,7 @@ def rasterize_views(*, means3D, opacities, viewmatrices, projmatrices, camposs, 
                             projmatrices=projmatrices[sl], camposs=camposs[sl], tanfovx=list(tanfovx)[sl], tanfovy=list(tanfovy)[sl],
                             image_height=image_height, image_width=image_width, bg=bg, sh_degree=sh_degree, shs=shs,
                             colors_precomp=colors_precomp, scales=scales, rotations=rotations, cov3D_precomp=cov3D_precomp,
-                            means2D=means2D[sl], scale_modifier=scale_modifier) for sl in (slice(0, h), slice(h, V))]
+                            means2D=means2D[sl], scale_modifier=scale_modifier, raw=raw) for sl in (slice(0, h), slice(h, V))]
     return tuple(torch.cat([o[k] for o in outs], 0) for k in range(4))
 
 
@@ -496,11 +503,11 @@ def _split_packed(flat: torch.Tensor, P: int, M: int):
 class _RasterizePacked(torch.autograd.Function):
     @staticmethod
     def forward(ctx, packed, means2D, P, M, cams):
-        bg, viewmatrix, projmatrix, campos, tanx, tany, H, W, deg, mod = cams
+        bg, viewmatrix, projmatrix, campos, tanx, tany, H, W, deg, mod, raw = cams
         dev = packed.device
         xyz, sc, rot, op, sh = _split_packed(packed.detach(), P, M)
         camt = [_f32c(t, dev) for t in (bg, viewmatrix, projmatrix, campos)]
-        color, radii, depth, alpha, st = _forward_impl(xyz, sh, None, op, sc, rot, None, *camt, tanx, tany, H, W, deg, mod)
+        color, radii, depth, alpha, st = _forward_impl(xyz, sh, None, op, sc, rot, None, *camt, tanx, tany, H, W, deg, mod, raw=raw)
         ctx.st, ctx.P, ctx.M = st, P, M
         ctx.save_for_backward(packed, *camt)
         ctx.mark_non_differentiable(radii)
@@ -521,10 +528,14 @@ class _RasterizePacked(torch.autograd.Function):
 
 
 def rasterize_views_packed(packed: torch.Tensor, P: int, sh_coeffs: int, *, viewmatrices, projmatrices, camposs, tanfovx, tanfovy,
-                           image_height, image_width, bg, sh_degree=0, means2D=None, scale_modifier=1.0):
+                           image_height, image_width, bg, sh_degree=0, means2D=None, scale_modifier=1.0, raw=False):
     """`rasterize_views` over ONE flat fp32 buffer [xyz 3P | scales 3P | rotations 4P | opacities P | shs 3*K*P], each
-    field starting on a 16-byte boundary (`packed_layout`; post-activation values; what `dist.pack` produces, broadcast
-    once per parameter version).  The backward
+    field starting on a 16-byte boundary (`packed_layout`; what `dist.pack` produces, broadcast once per parameter
+    version).  raw=False: post-activation values, as the rasteriser's classic inputs.  raw=True: the buffer holds the
+    optimiser's RAW parameters (log-scales, un-normalised quaternions, opacity logits; SH = cat(f_dc, f_rest)); the
+    activations of gaussian_model.py:95-118 and their Jacobians run inside the kernels, so `packed.grad` is the gradient
+    of the raw parameters and a training step needs no activation kernels, no pack copy and no autograd nodes besides
+    this one.  The backward
     kernels write the parameter gradients straight into one buffer of the same layout, which becomes `packed.grad`
     as is: no per-tensor gradient accumulation, and on several GPUs that buffer is the all-reduce payload in place.
     V <= MAX_VIEWS.  Returns color [V,3,H,W], radii [V,P], depth [V,1,H,W], alpha [V,1,H,W]."""
@@ -538,7 +549,7 @@ def rasterize_views_packed(packed: torch.Tensor, P: int, sh_coeffs: int, *, view
     if means2D is None:
         means2D = torch.zeros(V, P, 3, dtype=torch.float32, device=packed.device)
     cams = (bg, viewmatrices, projmatrices, camposs, list(tanfovx), list(tanfovy), int(image_height), int(image_width),
-            int(sh_degree), float(scale_modifier))
+            int(sh_degree), float(scale_modifier), bool(raw))
     try:
         return _RasterizePacked.apply(packed, means2D, int(P), int(sh_coeffs), cams)
     except InstanceLimitError:
@@ -548,7 +559,7 @@ def rasterize_views_packed(packed: torch.Tensor, P: int, sh_coeffs: int, *, view
     outs = [rasterize_views_packed(packed, P, sh_coeffs, viewmatrices=viewmatrices[sl], projmatrices=projmatrices[sl], camposs=camposs[sl],
                                    tanfovx=list(tanfovx)[sl], tanfovy=list(tanfovy)[sl], image_height=image_height,
                                    image_width=image_width, bg=bg, sh_degree=sh_degree, means2D=means2D[sl],
-                                   scale_modifier=scale_modifier) for sl in (slice(0, h), slice(h, V))]
+                                   scale_modifier=scale_modifier, raw=raw) for sl in (slice(0, h), slice(h, V))]
     return tuple(torch.cat([o[k] for o in outs], 0) for k in range(4))
 
 

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200GS_ABI_VERSION 2
+#define B200GS_ABI_VERSION 3
 #define B200GS_MAX_VIEWS 64 /* per call; callers chunk larger batches */
 
 typedef enum b200gs_status {
@@ -66,6 +66,11 @@ typedef struct b200gs_params {
     int32_t means3D_per_view; /* 0: means3D is [P,3], shared by all views (SDS batch).  1: means3D is [V,P,3] -- every
                                * view has its own positions, everything else shared: the animation frame batch
                                * (animation.py:383-403 moves only xyz between frames).  dL_dmeans3D then is [V,P,3]. */
+    int32_t raw_params;       /* 0: opacities / scales / rotations are post-activation values, as upstream's rasteriser takes them.
+                               * 1: they are GaussianModel's RAW parameters (_opacity logits, _scaling logs, un-normalised _rotation);
+                               * the getters' sigmoid / exp / F.normalize (scene/gaussian_model.py:95-118) are applied inside the
+                               * preprocess kernel and their Jacobians inside the backward kernel, so dL_dopacity / dL_dscales /
+                               * dL_drots are gradients w.r.t. the raw tensors.  cov3D_precomp is unaffected. */
 } b200gs_params;
 
 /* ---- buffer sizing (bytes).  The caller owns three opaque state buffers, exactly as upstream's

@@ -18,6 +18,7 @@ from humangaussian_b200.scene import sample_ply_scene, synthetic_body
 
 V = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 scene = sys.argv[2] if len(sys.argv) > 2 else "sample"
+per_view = len(sys.argv) > 3 and sys.argv[3] == "pv"  # V single-view calls per step (the reference's calling pattern)
 P, HW, deg = 300000, 1024, 3
 dev = "cuda:0"
 p = (sample_ply_scene(P, deg) if scene == "sample" else synthetic_body(P, sh_degree=deg, seed=0)).to(dev)
@@ -33,6 +34,13 @@ gw = [torch.randn(V, c, HW, HW, device=dev, generator=g) for c in (3, 1, 1)]
 
 
 def step():
+    if per_view:
+        outs = [R.rasterize_views(means3D=xyz, opacities=op, viewmatrices=vm[i:i + 1], projmatrices=pm[i:i + 1], camposs=cp[i:i + 1],
+                                  tanfovx=tanx[i:i + 1], tanfovy=tany[i:i + 1], image_height=HW, image_width=HW, bg=bg, sh_degree=deg,
+                                  shs=sh, scales=sc, rotations=rot) for i in range(V)]
+        for i, (c, r, d, a) in enumerate(outs):
+            torch.autograd.backward([c, d, a], [g[i:i + 1] for g in gw])
+        return torch.cat([o[1] for o in outs], 0)
     c, r, d, a = R.rasterize_views(means3D=xyz, opacities=op, viewmatrices=vm, projmatrices=pm, camposs=cp, tanfovx=tanx, tanfovy=tany,
                                    image_height=HW, image_width=HW, bg=bg, sh_degree=deg, shs=sh, scales=sc, rotations=rot)
     torch.autograd.backward([c, d, a], gw)
@@ -44,7 +52,7 @@ counters = hasattr(L, "b200gs_debug_counters")
 for _ in range(3):
     step()
 torch.cuda.synchronize()
-out = {"scene": scene, "V": V, "lib": os.path.basename(R.LIB_PATH)}
+out = {"scene": scene, "V": V, "per_view": per_view, "lib": os.path.basename(R.LIB_PATH)}
 if counters:
     buf = (C.c_ulonglong * 16)()
     L.b200gs_debug_counters(buf, 1)

@@ -35,7 +35,7 @@ def test_size_queries_are_sane(lib):
     lib.b200gs_image_bytes.restype = sz; lib.b200gs_image_bytes.argtypes = [i32, i32, i32]
     lib.b200gs_binning_bytes.restype = sz; lib.b200gs_binning_bytes.argtypes = [i64, i32, i32, i32, i32]
     lib.b200gs_backward_scratch_bytes.restype = sz; lib.b200gs_backward_scratch_bytes.argtypes = [i32, i32]
-    assert lib.b200gs_abi_version() == 2
+    assert lib.b200gs_abi_version() == 3
     assert lib.b200gs_geom_bytes(1000, 1) >= 1000 * (48 + 4 + 4 + 8 + 1)
     assert lib.b200gs_geom_bytes(1000, 4) >= 4 * 1000 * 65
     assert lib.b200gs_image_bytes(64, 64, 2) >= 2 * 64 * 64 * 8

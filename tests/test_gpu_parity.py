@@ -321,3 +321,60 @@ def test_render_views_feeds_reference_optimizer_hook():
         close(pkg["viewspace_points"].grad.sum(0).cpu().numpy(), viewspace_point_tensor_grad.cpu().numpy())[0]
     ok, worst = close(pb.xyz.grad.cpu().numpy(), pa.xyz.grad.cpu().numpy())
     assert ok, worst
+
+
+@pytest.mark.parametrize("deg", [0, 3])
+def test_fused_raw_activations_match_torch_activations_and_autograd(deg):
+    """raw=True applies exp / F.normalize / sigmoid (gaussian_model.py:95-118) inside F1 and their Jacobians
+    (incl. normalize's, which the reference gets from autograd) inside B3.  Against torch activations + autograd through
+    the classic entry: images to the north-star tolerance, gradients w.r.t. the RAW tensors by the gradient criterion."""
+    from humangaussian_b200.cameras import sample_orbit_cameras
+    from humangaussian_b200.rasterizer import packed_layout, rasterize_views, rasterize_views_packed
+    from humangaussian_b200.renderer import stack_cameras
+    from humangaussian_b200.scene import synthetic_body
+    P, H, W, V = 1500, 72, 104, 3
+    K = (deg + 1) ** 2
+    p = synthetic_body(P, sh_degree=deg, seed=21)
+    p.scaling += math.log(6.0)
+    p.opacity += 1.5
+    p = p.to(DEV)
+    cams = sample_orbit_cameras(V, H, W, seed=2, device=DEV)
+    vm, pm, cp, tanx, tany = stack_cameras(cams, DEV)
+    bg = torch.tensor([0.1, 0.4, 0.7], device=DEV)
+    rng = np.random.RandomState(1)
+    gw = [torch.tensor(rng.randn(V, c, H, W).astype(np.float32), device=DEV) for c in (3, 1, 1)]
+    kw = dict(viewmatrices=vm, projmatrices=pm, camposs=cp, tanfovx=tanx, tanfovy=tany, image_height=H, image_width=W, bg=bg, sh_degree=deg)
+    # reference chain: torch activations (the getters) + autograd
+    raw = {k: getattr(p, k).clone().requires_grad_(True) for k in ("xyz", "scaling", "rotation", "opacity", "features_dc", "features_rest")}
+    sh = torch.cat((raw["features_dc"], raw["features_rest"]), dim=1)
+    c0, r0, d0, a0 = rasterize_views(means3D=raw["xyz"], opacities=torch.sigmoid(raw["opacity"]), shs=sh, scales=torch.exp(raw["scaling"]),
+                                     rotations=torch.nn.functional.normalize(raw["rotation"]), **kw)
+    ((c0 * gw[0]).sum() + (d0 * gw[1]).sum() + (a0 * gw[2]).sum()).backward()
+    # fused: raw tensors straight in (unpacked entry) ...
+    raw2 = {k: getattr(p, k).clone().requires_grad_(True) for k in raw}
+    sh2 = torch.cat((raw2["features_dc"], raw2["features_rest"]), dim=1)
+    c1, r1, d1, a1 = rasterize_views(means3D=raw2["xyz"], opacities=raw2["opacity"], shs=sh2, scales=raw2["scaling"], rotations=raw2["rotation"],
+                                     raw=True, **kw)
+    ((c1 * gw[0]).sum() + (d1 * gw[1]).sum() + (a1 * gw[2]).sum()).backward()
+    assert torch.equal(r0, r1)
+    for x, y in ((c0, c1), (d0, d1), (a0, a1)):
+        ok, worst = close(y.detach().cpu().numpy(), x.detach().cpu().numpy())
+        assert ok, f"fused-activation image differs ({worst:.2f}x tolerance)"
+    for k in raw:
+        ok, msg = grads_agree(raw2[k].grad.cpu().numpy(), raw[k].grad.cpu().numpy())
+        assert ok, f"raw dL/d{k}: {msg}"
+    # ... and through the packed entry: flat.grad IS the raw-parameter gradient
+    fields, n = packed_layout(P, K)
+    flat = torch.zeros(n, device=DEV)
+    with torch.no_grad():
+        for (o, m, _), t in zip(fields, (p.xyz, p.scaling, p.rotation, p.opacity, torch.cat((p.features_dc, p.features_rest), 1))):
+            flat.narrow(0, o, m).copy_(t.reshape(-1))
+    flat.requires_grad_(True)
+    c2, r2, d2, a2 = rasterize_views_packed(flat, P, K, raw=True, **kw)
+    ((c2 * gw[0]).sum() + (d2 * gw[1]).sum() + (a2 * gw[2]).sum()).backward()
+    assert torch.equal(c2, c1) and torch.equal(d2, d1) and torch.equal(a2, a1)
+    ref = [raw["xyz"].grad, raw["scaling"].grad, raw["rotation"].grad, raw["opacity"].grad,
+           torch.cat((raw["features_dc"].grad, raw["features_rest"].grad), 1)]
+    for (o, m, shape), g in zip(fields, ref):
+        ok, msg = grads_agree(flat.grad.narrow(0, o, m).view(shape).cpu().numpy().reshape(P, -1), g.cpu().numpy().reshape(P, -1))
+        assert ok, f"packed raw gradient field at {o}: {msg}"
