@@ -66,7 +66,7 @@ size_t b200gs_binning_bytes(int64_t cap, int32_t H, int32_t W, int32_t P, int32_
     const int gx = (W + GS_TILE - 1) / GS_TILE, gy = (H + GS_TILE - 1) / GS_TILE;
     return binning_layout(cap, gx * gy * V, (int64_t)P * V).total;
 }
-size_t b200gs_backward_scratch_bytes(int32_t P, int32_t V) { return gs_align((size_t)P * V * sizeof(ScreenGrad)); }
+size_t b200gs_backward_scratch_bytes(int32_t P, int32_t V) { return gs_align((size_t)P * V * GS_SGRAD_BYTES_MAX); }
 
 static int check_common(const b200gs_params *p, const float *shs, const float *colors, const float *scales,
                         const float *rots, const float *cov)
@@ -194,7 +194,8 @@ int b200gs_backward(const b200gs_params *prm, const float *means3D, const float 
     if ((((uintptr_t)geom_buf) | ((uintptr_t)binning_buf) | ((uintptr_t)image_buf) | ((uintptr_t)scratch)) & 15) return B200GS_E_BUFFER;
     const char *gb = (const char *)geom_buf, *bb = (const char *)binning_buf, *ib = (const char *)image_buf;
 
-    CK(cudaMemsetAsync(scratch, 0, (size_t)P * V * sizeof(ScreenGrad), st), "memset scratch");
+    const size_t sg_bytes = blend_sgrad_is_moments() == 2 ? (size_t)GS_SGRAD_F64_DOUBLES * 8 : sizeof(ScreenGrad);
+    CK(cudaMemsetAsync(scratch, 0, (size_t)P * V * sg_bytes, st), "memset scratch");
     BlendBwdArgs b;
     b.H = H; b.W = W; b.grid_x = gx; b.grid_y = gy; b.V = V; b.P = P;
     b.ranges = (const uint2 *)(bb + BL.ranges); b.point_list = (const uint32_t *)(bb + BL.vals_out);
@@ -202,7 +203,7 @@ int b200gs_backward(const b200gs_params *prm, const float *means3D, const float 
     b.recs = (const GeomRec *)(gb + GL.recs); b.bg = bg;
     b.final_T = (const float *)(ib + IL.final_T); b.n_contrib = (const uint32_t *)(ib + IL.n_contrib);
     b.dL_dcolor = dL_dcolor; b.dL_ddepth = dL_ddepth; b.dL_dalpha = dL_dalpha;
-    b.sgrad = (ScreenGrad *)scratch;
+    b.sgrad = scratch;
     { StageTimer t(B200GS_STAGE_BLEND_BWD, st); launch_blend_bwd(b, st); }
 
     PreBwdArgs a;
@@ -213,7 +214,7 @@ int b200gs_backward(const b200gs_params *prm, const float *means3D, const float 
     a.means = means3D; a.shs = shs; a.colors_pre = colors_precomp; a.scales = scales; a.rots = rotations; a.cov_pre = cov3D_precomp;
     a.view = viewmatrix; a.proj = projmatrix; a.campos = campos;
     for (int v = 0; v < V; v++) { a.tanfovx[v] = prm->tanfovx[v]; a.tanfovy[v] = prm->tanfovy[v]; }
-    a.radii = radii; a.clamped = (const uint8_t *)(gb + GL.clamped); a.sgrad = (const ScreenGrad *)scratch;
+    a.radii = radii; a.clamped = (const uint8_t *)(gb + GL.clamped); a.sgrad = scratch;
     a.recs = (const GeomRec *)(gb + GL.recs); a.moments = blend_sgrad_is_moments();
     a.dL_dmeans3D = dL_dmeans3D; a.dL_dmeans2D = dL_dmeans2D; a.dL_dsh = dL_dsh; a.dL_dcolors = dL_dcolors;
     a.dL_dopacity = dL_dopacity; a.dL_dscales = dL_dscales; a.dL_drots = dL_drots; a.dL_dcov3D = dL_dcov3D;

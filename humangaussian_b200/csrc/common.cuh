@@ -86,6 +86,11 @@ struct __align__(16) ScreenGrad {
     float pad0, pad1;
 };
 static_assert(sizeof(ScreenGrad) == 48, "ScreenGrad must be 48 bytes");
+// The product's backward blend accumulates the ten sums in DOUBLE (red.global.add.f64): a Gaussian that covers thousands of
+// patches otherwise sums thousands of float32 partials in arrival order, and at BASELINE sizes a handful of the 300 k rows
+// left the 1e-4 tolerance (measured: worst row 2.2x with float accumulators).  96 B per (view, Gaussian).
+#define GS_SGRAD_F64_DOUBLES 12
+#define GS_SGRAD_BYTES_MAX 96
 
 __host__ __device__ inline size_t gs_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 

@@ -32,9 +32,10 @@ struct PreBwdArgs {
     float tanfovx[GS_MAX_VIEWS], tanfovy[GS_MAX_VIEWS];
     const int32_t *radii;
     const uint8_t *clamped;
-    const ScreenGrad *sgrad; // [V*P]
+    const void *sgrad;       // [V*P] ScreenGrad (float, 48 B) or 12 doubles (96 B), see `moments`
     const GeomRec *recs;     // [V*P] forward records (conic, opacity) -- used when sgrad holds moments
-    int moments;             // 1: sgrad = (S0,Sx,Sy,Sxx,Sxy,Syy,cr,cg,cb,cd); 0: classic (dx,dy,dA,dBh,dC,dO,dr,dg,db,dd)
+    int moments;             // 0: classic float (dx,dy,dA,dBh,dC,dO,dr,dg,db,dd); 1: float moments (S0,Sx,Sy,Sxx,Sxy,Syy,cr,cg,cb,cd);
+                             // 2: the same ten moments as doubles
     float *dL_dmeans3D, *dL_dmeans2D, *dL_dsh, *dL_dcolors, *dL_dopacity, *dL_dscales, *dL_drots, *dL_dcov3D;
 };
 
@@ -60,7 +61,7 @@ struct BlendBwdArgs {
     const float *final_T;
     const uint32_t *n_contrib;
     const float *dL_dcolor, *dL_ddepth, *dL_dalpha; // may be null
-    ScreenGrad *sgrad;                              // [V*P], zeroed by the caller
+    void *sgrad;                                    // [V*P] accumulators (format: blend_sgrad_is_moments()), zeroed by the caller
 };
 
 void launch_preprocess_fwd(const PreArgs &a, int V, cudaStream_t st);

@@ -305,7 +305,7 @@ void launch_mark_visible(int P, const float *pos, const float *V, uint8_t *prese
 // (deterministic: no atomics at the parameter level).  Plain float arithmetic (tolerance-compared).
 // ------------------------------------------------------------------------------------------------
 #ifndef PBWD_MIN_BLOCKS
-#define PBWD_MIN_BLOCKS 4 // swept on B200: 128 registers (a few spills) beats 227 registers at 8 warps/SM
+#define PBWD_MIN_BLOCKS 6 // 85 registers: the SH coefficients are re-read per view (L1/L2 hits) instead of living in 48 registers
 #endif
 template <int DEG>
 __global__ void __launch_bounds__(128, PBWD_MIN_BLOCKS) preprocess_bwd_kernel(PreBwdArgs a)
@@ -336,18 +336,53 @@ __global__ void __launch_bounds__(128, PBWD_MIN_BLOCKS) preprocess_bwd_kernel(Pr
     const float S[3][3] = {{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}};
 
     float dmean[3] = {0, 0, 0}, dcov[6] = {0, 0, 0, 0, 0, 0}, dop = 0.f, dcol[3] = {0, 0, 0};
-    float dsh[3 * nb], shc[3 * nb]; // SH gradient accumulators and the coefficients themselves, in registers
+    float dsh[3 * nb]; // SH gradient accumulators, in registers
 #pragma unroll
     for (int k = 0; k < 3 * nb; k++) dsh[k] = 0.f;
-    if (DEG >= 0) {
-        const float *sh = a.shs + (size_t)i * a.M * 3;
-#pragma unroll
-        for (int k = 0; k < 3 * nb; k++) shc[k] = __ldg(sh + k);
+    const float *shp = DEG >= 0 ? a.shs + (size_t)i * a.M * 3 : nullptr; // coefficients: re-read per view (12 x 16 B, L1-resident)
+    const bool sh16 = DEG >= 0 && (3 * nb) % 4 == 0 && (a.M & 3) == 0 && ((((uintptr_t)a.shs) & 15) == 0);
+
+    // Software pipeline over the views: the kernel is latency-bound (one dependent gather per view), so the radius of view
+    // v+2 and the 64 bytes of per-view state of view v+1 are requested before view v is reduced.
+    const float4 *sg4 = reinterpret_cast<const float4 *>(a.sgrad);
+    const double2 *sd2 = reinterpret_cast<const double2 *>(a.sgrad);
+    const float4 *rc4 = reinterpret_cast<const float4 *>(a.recs);
+    const bool f64 = a.moments == 2;
+    // the ten accumulated sums of one (view, Gaussian): 3 x 16 B of floats, or 5 x 16 B of doubles rounded to float here
+    auto load_sums = [&](size_t rec, float4 &o0, float4 &o1, float4 &o2) {
+        if (f64) {
+            const double2 d0 = __ldg(sd2 + 6 * rec), d1 = __ldg(sd2 + 6 * rec + 1), d2 = __ldg(sd2 + 6 * rec + 2),
+                          d3 = __ldg(sd2 + 6 * rec + 3), d4 = __ldg(sd2 + 6 * rec + 4);
+            o0 = make_float4((float)d0.x, (float)d0.y, (float)d1.x, (float)d1.y);
+            o1 = make_float4((float)d2.x, (float)d2.y, (float)d3.x, (float)d3.y);
+            o2 = make_float4((float)d4.x, (float)d4.y, 0.f, 0.f);
+        } else {
+            o0 = __ldg(sg4 + 3 * rec); o1 = __ldg(sg4 + 3 * rec + 1); o2 = __ldg(sg4 + 3 * rec + 2);
+        }
+    };
+    int rad_n = a.radii[i], rad_nn = a.V > 1 ? a.radii[(size_t)a.P + i] : 0;
+    float4 n0 = make_float4(0, 0, 0, 0), n1 = n0, n2 = n0, nr = n0;
+    uint8_t ncl = 0;
+    if (rad_n > 0) {
+        load_sums((size_t)i, n0, n1, n2);
+        nr = __ldg(rc4 + 3 * (size_t)i + 1);
+        ncl = a.clamped[i];
     }
 
     for (int v = 0; v < a.V; v++) {
         const size_t vp = (size_t)v * a.P + i;
         float *m2d = a.dL_dmeans2D + 3 * vp;
+        const int rad = rad_n;
+        const float4 g0 = n0, g1 = n1, g2 = n2, r1 = nr;
+        const uint8_t cl = ncl;
+        rad_n = rad_nn;
+        rad_nn = v + 2 < a.V ? a.radii[vp + 2 * (size_t)a.P] : 0;
+        if (rad_n > 0) {
+            const size_t vn = vp + (size_t)a.P;
+            load_sums(vn, n0, n1, n2);
+            nr = __ldg(rc4 + 3 * vn + 1);
+            ncl = a.clamped[vn];
+        }
         if (a.means_view_stride) { // per-view positions: per-view (not summed) position gradients
             if (v > 0) {
                 float *o = a.dL_dmeans3D + 3 * ((size_t)(v - 1) * a.P + i);
@@ -357,16 +392,13 @@ __global__ void __launch_bounds__(128, PBWD_MIN_BLOCKS) preprocess_bwd_kernel(Pr
                 px = m[0]; py = m[1]; pz = m[2];
             }
         }
-        if (!(a.radii[vp] > 0)) {
+        if (!(rad > 0)) {
             m2d[0] = 0.f; m2d[1] = 0.f; m2d[2] = 0.f;
             continue;
         }
-        const float4 *gp = reinterpret_cast<const float4 *>(a.sgrad + vp);
-        const float4 g0 = gp[0], g1 = gp[1], g2 = gp[2];
         float gdx, gdy, dA, dBh, dC, gO;
         if (a.moments) {
-            // moments of q = G*dL/dalpha over the Gaussian's pixels -> screen-space gradients (A.5)
-            const float4 r1 = reinterpret_cast<const float4 *>(a.recs + vp)[1]; // conic A,B,C and opacity
+            // moments of q = G*dL/dalpha over the Gaussian's pixels -> screen-space gradients (A.5); r1 = conic A,B,C and opacity
             const float S0 = g0.x, Sx = g0.y, Sy = g0.z, Sxx = g0.w, Sxy = g1.x, Syy = g1.y;
             gO = S0;
             gdx = -r1.w * (r1.x * Sx + r1.y * Sy) * (0.5f * (float)a.W);
@@ -456,7 +488,6 @@ __global__ void __launch_bounds__(128, PBWD_MIN_BLOCKS) preprocess_bwd_kernel(Pr
             const float x = ddx0 / len, y = ddy0 / len, z = ddz0 / len;
             float bs[16];
             sh_basis(DEG, x, y, z, bs);
-            const uint8_t cl = a.clamped[vp];
             const float dRGB[3] = {(cl & 1) ? 0.f : gcol[0], (cl & 2) ? 0.f : gcol[1], (cl & 4) ? 0.f : gcol[2]};
             float sk[16];
 #pragma unroll
@@ -464,7 +495,24 @@ __global__ void __launch_bounds__(128, PBWD_MIN_BLOCKS) preprocess_bwd_kernel(Pr
                 dsh[3 * k] += bs[k] * dRGB[0];
                 dsh[3 * k + 1] += bs[k] * dRGB[1];
                 dsh[3 * k + 2] += bs[k] * dRGB[2];
-                sk[k] = shc[3 * k] * dRGB[0] + shc[3 * k + 1] * dRGB[1] + shc[3 * k + 2] * dRGB[2];
+            }
+            if (DEG > 0) { // sk[k] = sh_k . dRGB, for the view-direction derivative: four coefficients (3 x 16 B) at a time
+                if (sh16) {
+#pragma unroll
+                    for (int kk = 0; kk < nb / 4; kk++) {
+                        const float4 t0 = __ldg(reinterpret_cast<const float4 *>(shp) + 3 * kk);
+                        const float4 t1 = __ldg(reinterpret_cast<const float4 *>(shp) + 3 * kk + 1);
+                        const float4 t2 = __ldg(reinterpret_cast<const float4 *>(shp) + 3 * kk + 2);
+                        sk[4 * kk] = t0.x * dRGB[0] + t0.y * dRGB[1] + t0.z * dRGB[2];
+                        sk[4 * kk + 1] = t0.w * dRGB[0] + t1.x * dRGB[1] + t1.y * dRGB[2];
+                        sk[4 * kk + 2] = t1.z * dRGB[0] + t1.w * dRGB[1] + t2.x * dRGB[2];
+                        sk[4 * kk + 3] = t2.y * dRGB[0] + t2.z * dRGB[1] + t2.w * dRGB[2];
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < nb; k++)
+                        sk[k] = __ldg(shp + 3 * k) * dRGB[0] + __ldg(shp + 3 * k + 1) * dRGB[1] + __ldg(shp + 3 * k + 2) * dRGB[2];
+                }
             }
             if (DEG > 0) {
                 float ddx = -SH_C1 * sk[3], ddy = -SH_C1 * sk[1], ddz = SH_C1 * sk[2];

@@ -121,6 +121,28 @@ def load_library():
     return L
 
 
+class use_library:
+    """Context manager: run the SAME host path against another build of the C-ABI (bench.py times
+    baseline/libb200gs_classic.so, the classic-structure CUDA comparator, next to the product in one process).
+    Not a fallback mechanism: outside the `with` block the product library is back."""
+
+    def __init__(self, path):
+        self.path = path
+
+    def __enter__(self):
+        global _lib, LIB_PATH
+        self.saved = (_lib, LIB_PATH)
+        _lib, LIB_PATH = None, self.path
+        _pool.clear()
+        return load_library()
+
+    def __exit__(self, *exc):
+        global _lib, LIB_PATH
+        _lib, LIB_PATH = self.saved
+        _pool.clear()
+        return False
+
+
 def launch_count() -> int:
     return int(load_library().b200gs_launch_count())
 

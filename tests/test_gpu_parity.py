@@ -314,13 +314,14 @@ def test_render_views_feeds_reference_optimizer_hook():
     for idx in range(len(viewspace_point_list)):
         viewspace_point_tensor_grad = viewspace_point_tensor_grad + viewspace_point_list[idx].grad
     assert viewspace_point_tensor_grad.shape == (3000, 3)
-    ok, worst = close(viewspace_point_tensor_grad.cpu().numpy(), grad_ref.cpu().numpy())
-    assert ok, worst
+    # two float32 evaluations with atomics in different orders: the gradient criterion (row-wise strict), not bit equality
+    ok, msg = grads_agree(viewspace_point_tensor_grad.cpu().numpy(), grad_ref.cpu().numpy())
+    assert ok, msg
     assert torch.equal(pkg["radii"].max(0).values, radii)
-    assert torch.equal(pkg["viewspace_points"].grad.sum(0), viewspace_point_tensor_grad) or \
-        close(pkg["viewspace_points"].grad.sum(0).cpu().numpy(), viewspace_point_tensor_grad.cpu().numpy())[0]
-    ok, worst = close(pb.xyz.grad.cpu().numpy(), pa.xyz.grad.cpu().numpy())
-    assert ok, worst
+    ok, msg = grads_agree(pkg["viewspace_points"].grad.sum(0).cpu().numpy(), viewspace_point_tensor_grad.cpu().numpy())
+    assert ok, msg
+    ok, msg = grads_agree(pb.xyz.grad.cpu().numpy(), pa.xyz.grad.cpu().numpy())
+    assert ok, msg
 
 
 @pytest.mark.parametrize("deg", [0, 3])
