@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(BLOCK_SIZE) classic_bwd(BlendBwdArgs a)
             const float dchannel_dcolor = alpha * T;
             float dL_dopa = 0.0f;
             const uint32_t gid = c_id[j];
-            float *sg = reinterpret_cast<float *>(a.sgrad + gid);
+            float *sg = reinterpret_cast<float *>(reinterpret_cast<ScreenGrad *>(a.sgrad) + gid);
             for (int ch = 0; ch < 3; ch++) {
                 const float c = c_col[ch * BLOCK_SIZE + j];
                 accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];

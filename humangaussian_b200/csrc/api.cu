@@ -42,6 +42,21 @@ struct StageTimer {
     }
 };
 
+// one pinned 8-byte word + event per (host thread, device): where the forward's instance count lands without a host wait
+struct HostSlot { unsigned long long *total; cudaEvent_t ev; };
+static HostSlot *host_slot()
+{
+    static thread_local HostSlot slots[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    HostSlot &s = slots[dev];
+    if (!s.total) {
+        if (cudaHostAlloc((void **)&s.total, 8, cudaHostAllocDefault) != cudaSuccess) { s.total = nullptr; return nullptr; }
+        if (cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming) != cudaSuccess) { cudaFreeHost(s.total); s.total = nullptr; return nullptr; }
+    }
+    return &s;
+}
+
 static int cuda_fail(cudaError_t e, const char *where)
 {
     snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
@@ -106,11 +121,12 @@ int b200gs_forward(const b200gs_params *prm, const float *means3D, const float *
     char *gb = (char *)geom_buf, *bb = (char *)binning_buf, *ib = (char *)image_buf;
     const size_t HW = (size_t)H * W;
     *num_rendered = 0;
+    HostSlot *pending = nullptr;
 
     if (P == 0) { // empty scene: background only
         CK(cudaMemsetAsync(bb + BL.ranges, 0, (size_t)gx * gy * V * 8, st), "memset ranges");
         int nl0 = 0;
-        if (launch_binning(nullptr, nullptr, nullptr, 0, V, gx, gy, 0, bb, BL, st, &nl0)) return cuda_fail(cudaGetLastError(), "binning");
+        if (launch_binning(nullptr, nullptr, nullptr, 0, V, gx, gy, 0, nullptr, bb, BL, st, &nl0)) return cuda_fail(cudaGetLastError(), "binning");
     } else {
         PreArgs a;
         a.P = P; a.deg = shs ? prm->sh_degree : 0; a.M = prm->sh_coeffs; a.H = H; a.W = W; a.grid_x = gx; a.grid_y = gy;
@@ -135,21 +151,24 @@ int b200gs_forward(const b200gs_params *prm, const float *means3D, const float *
             StageTimer t(B200GS_STAGE_SCAN, st);
             if (launch_depth_order(a.tiles_touched, offsets, n_vp, V, bb, BL, &order_sorted, &total_dev, st, &nl)) return cuda_fail(cudaGetLastError(), "depth order");
         }
-        // the EXACT 64-bit instance count (the 32-bit offsets may have wrapped: nothing reads them before this check)
-        uint64_t total = 0;
-        CK(cudaMemcpyAsync(&total, total_dev, 8, cudaMemcpyDeviceToHost, st), "D2H num_rendered");
-        CK(cudaStreamSynchronize(st), "sync after scan");
-        *num_rendered = (int64_t)total;
-        if (total > (uint64_t)B200GS_MAX_INSTANCES) return B200GS_E_INSTANCES;
-        if ((int64_t)total > instance_capacity) return B200GS_E_BIN_TOO_SMALL;
-        {
+        // The EXACT 64-bit instance count travels to a pinned host word asynchronously; the host does NOT wait for it here.
+        // Emit / tile sort / ranges / blend are enqueued sized for the caller's capacity and read the count on the device, so
+        // the GPU never idles behind a host round trip (upstream blocks on this read-back in the middle of every forward).
+        // The count is checked after the last launch, when the copy has long completed: a batch that did not fit produced
+        // clamped, in-bounds garbage and the call reports it (B200GS_E_BIN_TOO_SMALL / _E_INSTANCES) before anything is used.
+        HostSlot *hs = host_slot();
+        if (!hs) return cuda_fail(cudaGetLastError(), "pinned count slot");
+        CK(cudaMemcpyAsync(hs->total, total_dev, 8, cudaMemcpyDeviceToHost, st), "D2H num_rendered");
+        CK(cudaEventRecord(hs->ev, st), "event after count copy");
+        pending = hs;
+        const int64_t cap = instance_capacity < B200GS_MAX_INSTANCES ? instance_capacity : (int64_t)B200GS_MAX_INSTANCES;
+        if (cap > 0) {
             StageTimer t(B200GS_STAGE_BINNING, st);
-            const int brc = launch_binning(order_sorted, a.rects, offsets, P, V, gx, gy, (int64_t)total, bb, BL, st, &nl);
+            const int brc = launch_binning(order_sorted, a.rects, offsets, P, V, gx, gy, cap, total_dev, bb, BL, st, &nl);
             if (brc == -3) return B200GS_E_RANGE;
             if (brc) return cuda_fail(cudaGetLastError(), "binning");
         }
         g_launches += nl; // radix count/scan/scatter passes, tile scan, emit, ranges, tile order: all ours
-        // remember where the depth order landed (ping-pong parity) for b200gs_describe_state
     }
     BlendArgs b;
     b.H = H; b.W = W; b.grid_x = gx; b.grid_y = gy; b.V = V; b.P = P;
@@ -159,9 +178,19 @@ int b200gs_forward(const b200gs_params *prm, const float *means3D, const float *
     b.final_T = (float *)(ib + IL.final_T); b.n_contrib = (uint32_t *)(ib + IL.n_contrib);
     b.out_color = out_color; b.out_depth = out_depth; b.out_alpha = out_alpha;
     (void)HW;
-    { StageTimer t(B200GS_STAGE_BLEND_FWD, st); launch_blend_fwd(b, st); }
-    g_launches += 1;
+    if (!pending || instance_capacity > 0) {
+        StageTimer t(B200GS_STAGE_BLEND_FWD, st);
+        launch_blend_fwd(b, st);
+        g_launches += 1;
+    }
     CK(cudaGetLastError(), "forward launch");
+    if (pending) { // everything is enqueued; now look at the instance count (copied right after the scan)
+        CK(cudaEventSynchronize(pending->ev), "wait for the instance count");
+        const uint64_t total = *pending->total;
+        *num_rendered = (int64_t)total;
+        if (total > (uint64_t)B200GS_MAX_INSTANCES) return B200GS_E_INSTANCES;
+        if ((int64_t)total > instance_capacity) return B200GS_E_BIN_TOO_SMALL;
+    }
     return B200GS_OK;
 }
 

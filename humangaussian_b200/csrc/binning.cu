@@ -68,8 +68,8 @@ BinLayout binning_layout(int64_t capacity, int ntiles_total, int64_t n_vp)
 // Generic driver: stable LSD radix sort of n pairs over key bits [0, nbits).  Buffers a/b ping-pong; on return
 // *keys_sorted / *vals_sorted point at whichever buffer holds the result.  scratch must be sort_scratch_bytes().
 template <typename KeyT, int RBITS, int IPT>
-static int radix_sort_pairs(KeyT *ka, KeyT *kb, uint32_t *va, uint32_t *vb, int64_t n, int nbits, char *scratch, size_t scratch_bytes,
-                            KeyT **keys_sorted, uint32_t **vals_sorted, cudaStream_t st, int *n_launches)
+static int radix_sort_pairs(KeyT *ka, KeyT *kb, uint32_t *va, uint32_t *vb, int64_t n, const uint64_t *n_dev, int nbits, char *scratch,
+                            size_t scratch_bytes, KeyT **keys_sorted, uint32_t **vals_sorted, cudaStream_t st, int *n_launches)
 {
     constexpr int BINS = 1 << RBITS, TILE = THREADS * IPT;
     if (nbits < 1) nbits = 1;
@@ -84,9 +84,9 @@ static int radix_sort_pairs(KeyT *ka, KeyT *kb, uint32_t *va, uint32_t *vb, int6
     uint32_t *vin = va, *vout = vb;
     for (int p = 0; p < npass; p++) {
         const int bits = (p == npass - 1) ? last_bits : RBITS;
-        count_kernel<KeyT, RBITS, IPT><<<nblocks, THREADS, 0, st>>>(kin, n, p * RBITS, bits, counts, nblocks);
+        count_kernel<KeyT, RBITS, IPT><<<nblocks, THREADS, 0, st>>>(kin, n, n_dev, p * RBITS, bits, counts, nblocks);
         scan_counts_kernel<<<BINS, THREADS, 0, st>>>(counts, nblocks, totals);
-        scatter_kernel<KeyT, RBITS, IPT><<<nblocks, THREADS, 0, st>>>(kin, kout, vin, vout, n, p * RBITS, bits, counts, nblocks, totals);
+        scatter_kernel<KeyT, RBITS, IPT><<<nblocks, THREADS, 0, st>>>(kin, kout, vin, vout, n, n_dev, p * RBITS, bits, counts, nblocks, totals);
         KeyT *tk = kin; kin = kout; kout = tk;
         uint32_t *tv = vin; vin = vout; vout = tv;
     }
@@ -105,7 +105,7 @@ int launch_depth_order(const uint32_t *tiles_touched, uint32_t *offsets_sorted, 
     uint32_t *ks = nullptr, *vs = nullptr;
     if (radix_sort_pairs<uint32_t, D_BITS, D_IPT>((uint32_t *)(bin_base + L.dkeys_in), (uint32_t *)(bin_base + L.dkeys_out),
                                                   (uint32_t *)(bin_base + L.order_in), (uint32_t *)(bin_base + L.order), n_vp,
-                                                  32, bin_base + L.temp, L.temp_bytes, &ks, &vs, st, n_launches))
+                                                  nullptr, 32, bin_base + L.temp, L.temp_bytes, &ks, &vs, st, n_launches))
         return -1;
     *order_sorted = vs;
     const size_t nblocks = (size_t)((n_vp + SCAN_TILE - 1) / SCAN_TILE);
@@ -124,9 +124,10 @@ int launch_depth_order(const uint32_t *tiles_touched, uint32_t *offsets_sorted, 
 // (A thread-per-Gaussian loop writes 4-byte words 18 bytes apart on average: 1.1 TB/s, measured.)
 __global__ void __launch_bounds__(256) emit_tiles_kernel(const uint32_t *__restrict__ order, const uint2 *__restrict__ rects,
                                                           const uint32_t *__restrict__ offsets_sorted, int P, int64_t n_vp,
-                                                          int grid_x, int ntiles, uint32_t *__restrict__ keys,
+                                                          int grid_x, int ntiles, uint32_t cap, uint32_t *__restrict__ keys,
                                                           uint32_t *__restrict__ vals)
-{
+{   // cap: capacity of keys/vals.  The host launches this before it knows the instance count; if the batch turns out larger
+    // than the capacity the writes stop at cap (the call then reports B200GS_E_BIN_TOO_SMALL and is repeated with more room)
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     uint32_t vp = 0, x0 = 0, y0 = 0, w = 1, cnt = 0, end = 0;
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(256) emit_tiles_kernel(const uint32_t *__restr
         const uint32_t o_w = __shfl_sync(0xffffffffu, w, lo);
         const uint32_t o_base = __shfl_sync(0xffffffffu, tile_base, lo);
         const uint32_t o_vp = __shfl_sync(0xffffffffu, vp, lo);
-        if (j < warp_end) {
+        if (j < warp_end && j < cap) {
             const uint32_t local = j - o_start;
             const uint32_t dy = local / o_w, dx = local - dy * o_w;
             keys[j] = o_base + dy * (uint32_t)grid_x + dx;
@@ -168,8 +169,10 @@ __global__ void __launch_bounds__(256) emit_tiles_kernel(const uint32_t *__restr
 }
 
 // tile boundaries of the sorted keys: four keys per thread (one 128-bit load + the neighbour before)
-__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t *__restrict__ keys, int64_t D, uint2 *__restrict__ ranges)
+__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t *__restrict__ keys, int64_t D, const uint64_t *__restrict__ D_dev,
+                                                           uint2 *__restrict__ ranges)
 {
+    if (D_dev) D = min(D, (int64_t)*D_dev);
     const int64_t j0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (j0 >= D) return;
     uint32_t t[4];
@@ -237,8 +240,10 @@ __global__ void __launch_bounds__(256) tile_bucket_scatter_kernel(const uint2 *_
 
 // After this call the sorted tile keys are at bin_base+L.keys_out and the point list at bin_base+L.vals_out
 // (a device-to-device copy fixes the parity when the number of passes is even).
+// D: the instance count if the host knows it (D_dev == nullptr), else the CAPACITY the launches are sized for while the real
+// count is read by the kernels from *D_dev (no host synchronisation between the scan and the sort).
 int launch_binning(const uint32_t *order_sorted, const uint2 *rects, const uint32_t *offsets_sorted, int P, int V, int grid_x, int grid_y,
-                   int64_t D, char *bin_base, const BinLayout &L, cudaStream_t st, int *n_launches)
+                   int64_t D, const uint64_t *D_dev, char *bin_base, const BinLayout &L, cudaStream_t st, int *n_launches)
 {
     const int ntiles = grid_x * grid_y;
     const int64_t n_vp = (int64_t)P * V;
@@ -261,11 +266,11 @@ int launch_binning(const uint32_t *order_sorted, const uint2 *rects, const uint3
     // emit into the buffer from which `npass` ping-pong passes end in keys_out/vals_out
     uint32_t *k0 = (npass & 1) ? keys_in : keys_out, *k1 = (npass & 1) ? keys_out : keys_in;
     uint32_t *v0 = (npass & 1) ? vals_in : vals_out, *v1 = (npass & 1) ? vals_out : vals_in;
-    emit_tiles_kernel<<<(unsigned)((n_vp + 255) / 256), 256, 0, st>>>(order_sorted, rects, offsets_sorted, P, n_vp, grid_x, ntiles, k0, v0);
+    emit_tiles_kernel<<<(unsigned)((n_vp + 255) / 256), 256, 0, st>>>(order_sorted, rects, offsets_sorted, P, n_vp, grid_x, ntiles, (uint32_t)D, k0, v0);
     uint32_t *ks = nullptr, *vs = nullptr;
-    if (radix_sort_pairs<uint32_t, T_BITS, T_IPT>(k0, k1, v0, v1, D, nbits, bin_base + L.temp, L.temp_bytes, &ks, &vs, st, n_launches)) return -2;
+    if (radix_sort_pairs<uint32_t, T_BITS, T_IPT>(k0, k1, v0, v1, D, D_dev, nbits, bin_base + L.temp, L.temp_bytes, &ks, &vs, st, n_launches)) return -2;
     if (ks != keys_out || vs != vals_out) return -4;
-    tile_ranges_kernel<<<(unsigned)((D + 1023) / 1024), 256, 0, st>>>(keys_out, D, ranges);
+    tile_ranges_kernel<<<(unsigned)((D + 1023) / 1024), 256, 0, st>>>(keys_out, D, D_dev, ranges);
     cudaMemsetAsync(tcnt, 0, 64 * 4, st);
     tile_bucket_count_kernel<<<(nt_all + 255) / 256, 256, 0, st>>>(ranges, nt_all, tcnt);
     tile_bucket_scatter_kernel<<<(nt_all + 255) / 256, 256, 0, st>>>(ranges, nt_all, tcnt, tile_order);
@@ -279,7 +284,7 @@ int launch_test_sort32(uint32_t *ka, uint32_t *kb, uint32_t *va, uint32_t *vb, i
 {
     uint32_t *ks = nullptr, *vs = nullptr;
     int nl = 0;
-    const int rc = radix_sort_pairs<uint32_t, T_BITS, T_IPT>(ka, kb, va, vb, n, nbits, scratch, scratch_bytes, &ks, &vs, st, &nl);
+    const int rc = radix_sort_pairs<uint32_t, T_BITS, T_IPT>(ka, kb, va, vb, n, nullptr, nbits, scratch, scratch_bytes, &ks, &vs, st, &nl);
     *result_in_b = (ks == kb);
     return rc;
 }

@@ -28,6 +28,15 @@
 #define BWD_MIN_BLOCKS 16 // caps the backward kernel at 64 registers (32 warps/SM); 18 / 20 blocks (55 / 48 regs) measured slower
 #endif
 #define CTAS_PER_TILE (8 / WARPS_PER_CTA)
+#ifndef BWD_ILP2
+#define BWD_ILP2 0 // backward: two hits per inner iteration (needs SLAB_PACK)
+#endif
+#ifndef FWD_ILP2
+#define FWD_ILP2 0 // forward: two hits per inner iteration (needs SLAB_PACK)
+#endif
+#ifndef FWD_BULK
+#define FWD_BULK 0 // 1: forward blend with cp.async.bulk + mbarrier staging of the id runs (A/B experiment)
+#endif
 #ifndef SGRAD_F64
 #define SGRAD_F64 1 // per-Gaussian accumulators in double (red.global.add.f64)
 #endif
@@ -67,6 +76,7 @@ struct __align__(16) WarpSlab {
 // ------------------------------------------------------------------------------------------------
 // F6
 // ------------------------------------------------------------------------------------------------
+#if !FWD_BULK
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_fwd_kernel(BlendArgs a)
 {
     __shared__ WarpSlab slabs[WARPS_PER_CTA];
@@ -132,6 +142,53 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_fwd_kernel(BlendArgs
         }
         __syncwarp();
         const int cnt = __popc(b);
+#if FWD_ILP2
+        // two hits per iteration: their powers / exps / alphas are independent instruction streams (the transmittance chain
+        // is only the few operations behind them), which is what a single warp walking a deep tile needs -- one view has a
+        // few long lists, not enough warps to hide a dependent chain.  An odd count is padded with a zero-opacity entry.
+        if ((cnt & 1) && lane == 0) { // finite centre + zero conic/opacity: power = 0, alpha = 0 -> skipped by the 1/255 test
+            sl.rec[3 * cnt] = make_float4(0.f, 0.f, 0.f, 0.f);
+            sl.rec[3 * cnt + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
+        for (int i = 0; i < cnt; i += 2) {
+            const float4 g0a = sl.rec[3 * i], q1a = sl.rec[3 * i + 1];
+            const float4 g0b = sl.rec[3 * i + 3], q1b = sl.rec[3 * i + 4];
+            const float dxa = fsub(g0a.x, fpx), dya = fsub(g0a.y, fpy), dxb = fsub(g0b.x, fpx), dyb = fsub(g0b.y, fpy);
+            const float pa = power_prescaled(q1a.x, q1a.y, q1a.z, dxa, dya), pb = power_prescaled(q1b.x, q1b.y, q1b.z, dxb, dyb);
+            const float aa = fminf(GS_ALPHA_MAX, fmul(q1a.w, gs_exp(pa))), ab = fminf(GS_ALPHA_MAX, fmul(q1b.w, gs_exp(pb)));
+            if (!(pa > 0.0f) && !(aa < GS_ALPHA_MIN)) {
+                const float test_T = fmul(T, fsub(1.0f, aa));
+                if (test_T < GS_T_MIN) {
+                    if (T != 0.0f) T_out = T;
+                    T = 0.0f;
+                } else {
+                    const float w = fmul(aa, T);
+                    const float4 q2 = sl.rec[3 * i + 2];
+                    C0 = ffma(q2.x, w, C0); C1 = ffma(q2.y, w, C1); C2 = ffma(q2.z, w, C2);
+                    Dd = ffma(q2.w, w, Dd);
+                    Aa = fadd(Aa, w);
+                    T = test_T;
+                    last = __float_as_uint(g0a.z);
+                }
+            }
+            if (!(pb > 0.0f) && !(ab < GS_ALPHA_MIN)) {
+                const float test_T = fmul(T, fsub(1.0f, ab));
+                if (test_T < GS_T_MIN) {
+                    if (T != 0.0f) T_out = T;
+                    T = 0.0f;
+                } else {
+                    const float w = fmul(ab, T);
+                    const float4 q2 = sl.rec[3 * i + 5];
+                    C0 = ffma(q2.x, w, C0); C1 = ffma(q2.y, w, C1); C2 = ffma(q2.z, w, C2);
+                    Dd = ffma(q2.w, w, Dd);
+                    Aa = fadd(Aa, w);
+                    T = test_T;
+                    last = __float_as_uint(g0b.z);
+                }
+            }
+        }
+#else
         for (int i = 0; i < cnt; i++) {
             const float4 g0 = sl.rec[3 * i], q1 = sl.rec[3 * i + 1];
             const float dx = fsub(g0.x, fpx), dy = fsub(g0.y, fpy);
@@ -159,6 +216,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_fwd_kernel(BlendArgs
                 }
             }
         }
+#endif
         __syncwarp();
     }
     if (inside) {
@@ -175,6 +233,177 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_fwd_kernel(BlendArgs
         a.out_alpha[v * HW + pix] = Aa;
     }
 }
+
+#endif // !FWD_BULK
+
+#if FWD_BULK
+// ------------------------------------------------------------------------------------------------
+// F6, bulk-copy variant (A/B experiment of round 2; DESIGN.md "Blackwell staging"): the tile's id run -- the one contiguous
+// stream of the blend -- is brought into shared memory by the async proxy (cp.async.bulk + mbarrier complete_tx, two 1 KB
+// stages per warp) instead of per-lane LDG prefetches; the 48-byte records are still gathered by id (they are scattered in
+// HBM: a bulk copy moves contiguous bytes only).  Chunks are aligned to the absolute 32-entry grid of point_list so that a
+// chunk never straddles two stages and every bulk copy starts on a 16-byte boundary; results are identical.
+// ------------------------------------------------------------------------------------------------
+#define BULK_CHUNKS 8                    // chunks (of 32 ids) per stage
+#define BULK_IDS (32 * BULK_CHUNKS)      // 256 ids = 1 KB per stage
+struct __align__(16) BulkStage {
+    uint32_t ids[2][BULK_IDS];
+    unsigned long long mbar[2];
+};
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *b)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(b)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, uint32_t parity)
+{
+    uint32_t done = 0;
+    int spins = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_addr(b)), "r"(parity) : "memory");
+        if (!done && ++spins > (1 << 24)) __trap(); // a protocol error must fail loudly, never hang the GPU
+    }
+}
+
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA) blend_fwd_kernel(BlendArgs a)
+{
+    __shared__ WarpSlab slabs[WARPS_PER_CTA];
+    __shared__ BulkStage bulk[WARPS_PER_CTA];
+
+    const int ntiles = a.grid_x * a.grid_y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t vt = a.tile_order[blockIdx.x / CTAS_PER_TILE];
+    const int v = (int)(vt / (uint32_t)ntiles), tile = (int)(vt % (uint32_t)ntiles);
+    const int patch = (blockIdx.x % CTAS_PER_TILE) * WARPS_PER_CTA + warp;
+    const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
+    const int x0 = tile_x * GS_TILE + (patch & 1) * 8, y0 = tile_y * GS_TILE + (patch >> 1) * 4;
+    const int px = x0 + (lane & 7), py = y0 + (lane >> 3);
+    const bool inside = px < a.W && py < a.H;
+    const float fpx = (float)px, fpy = (float)py, fx0 = (float)x0, fy0 = (float)y0;
+    WarpSlab &sl = slabs[warp];
+    BulkStage &bk = bulk[warp];
+
+    const uint2 range = a.ranges[(size_t)v * ntiles + tile];
+    const float4 *recs4 = reinterpret_cast<const float4 *>(a.recs);
+    const uint32_t lt = (1u << lane) - 1u;
+    // absolute chunk grid: chunk c covers point_list[a0 + 32 c + lane]
+    const uint32_t a0 = range.x & ~31u;
+    const int n_chunks = range.y > range.x ? (int)((range.y - a0 + 31u) >> 5) : 0;
+    const int n_stages = (n_chunks + BULK_CHUNKS - 1) / BULK_CHUNKS;
+
+    float T = inside ? 1.0f : 0.0f, T_out = 1.0f;
+    float C0 = 0.f, C1 = 0.f, C2 = 0.f, Dd = 0.f, Aa = 0.f;
+    uint32_t last = 0;
+
+    if (lane == 0) { mbar_init(&bk.mbar[0], 1); mbar_init(&bk.mbar[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    // stage s -> buffer s & 1, its (s >> 1)-th use: wait parity (s >> 1) & 1.  Bytes: whole stage, clipped to the 16-byte
+    // rounded end of the tile's run (inside the point_list allocation: its capacity is rounded up to 256 bytes).
+    auto issue = [&](int s) {
+        const uint32_t first = a0 + (uint32_t)s * BULK_IDS;
+        const uint32_t end = min(first + (uint32_t)BULK_IDS, (range.y + 3u) & ~3u);
+        bulk_load(bk.ids[s & 1], a.point_list + first, (end - first) * 4u, &bk.mbar[s & 1]);
+    };
+    int issued = 0, waited = 0; // stages issued / stages whose arrival has been observed (warp-uniform)
+    if (lane == 0) { if (n_stages > 0) issue(0); if (n_stages > 1) issue(1); }
+    issued = min(n_stages, 2);
+
+    uint32_t id_c = 0;
+    float4 g0_c = make_float4(0.f, 0.f, -1.f, -1.f);
+    bool valid_c = false;
+    if (n_chunks > 0) {
+        mbar_wait(&bk.mbar[0], 0);
+        waited = 1;
+        const uint32_t ab = a0 + lane;
+        valid_c = ab >= range.x && ab < range.y;
+        if (valid_c) { id_c = bk.ids[0][lane]; g0_c = __ldg(recs4 + 3 * (size_t)id_c); }
+    }
+    for (int c = 0; c < n_chunks; c++) {
+        if (__all_sync(FULL, T == 0.0f)) break;
+        const bool hit = box_hits_patch(g0_c, fx0, fy0);
+        const uint32_t b = __ballot_sync(FULL, hit);
+        float4 g1, g2;
+        if (hit) {
+            g1 = __ldg(recs4 + 3 * (size_t)id_c + 1);
+            g2 = __ldg(recs4 + 3 * (size_t)id_c + 2);
+        }
+        const float4 g0_h = g0_c;
+        const uint32_t pos_h = a0 + 32u * (uint32_t)c + lane - range.x + 1u; // 1-based list position
+        // next chunk: ids from the stage in shared memory (wait for it when the chunk opens a new stage), records by gather
+        g0_c = make_float4(0.f, 0.f, -1.f, -1.f);
+        if (c + 1 < n_chunks) {
+            const int sn = (c + 1) / BULK_CHUNKS;
+            if (sn == waited) { mbar_wait(&bk.mbar[sn & 1], (uint32_t)(sn >> 1) & 1u); waited = sn + 1; }
+            const uint32_t ab = a0 + 32u * (uint32_t)(c + 1) + lane;
+            if (ab >= range.x && ab < range.y) {
+                id_c = bk.ids[sn & 1][((c + 1) % BULK_CHUNKS) * 32 + lane];
+                g0_c = __ldg(recs4 + 3 * (size_t)id_c);
+            }
+            // the stage before `sn` was last read one iteration ago (the ballot above ordered those reads): refill its buffer
+            if ((c + 1) % BULK_CHUNKS == 0 && sn + 1 < n_stages && sn + 1 == issued) {
+                if (lane == 0) issue(sn + 1);
+                issued = sn + 2;
+            }
+        }
+        if (b == 0u) continue;
+        if (hit) {
+            const int slot = __popc(b & lt);
+            sl.rec[3 * slot] = make_float4(g0_h.x, g0_h.y, __uint_as_float(pos_h), 0.f);
+            sl.rec[3 * slot + 1] = make_float4(fmul(-0.5f, g1.x), -g1.y, fmul(-0.5f, g1.z), g1.w);
+            sl.rec[3 * slot + 2] = g2;
+        }
+        __syncwarp();
+        const int cnt = __popc(b);
+        for (int i = 0; i < cnt; i++) {
+            const float4 g0 = sl.rec[3 * i], q1 = sl.rec[3 * i + 1];
+            const float dx = fsub(g0.x, fpx), dy = fsub(g0.y, fpy);
+            const float power = power_prescaled(q1.x, q1.y, q1.z, dx, dy);
+            if (!(power > 0.0f)) {
+                const float alpha = fminf(GS_ALPHA_MAX, fmul(q1.w, gs_exp(power)));
+                if (!(alpha < GS_ALPHA_MIN)) {
+                    const float test_T = fmul(T, fsub(1.0f, alpha));
+                    if (test_T < GS_T_MIN) {
+                        if (T != 0.0f) T_out = T;
+                        T = 0.0f;
+                    } else {
+                        const float w = fmul(alpha, T);
+                        const float4 q2 = sl.rec[3 * i + 2];
+                        C0 = ffma(q2.x, w, C0); C1 = ffma(q2.y, w, C1); C2 = ffma(q2.z, w, C2);
+                        Dd = ffma(q2.w, w, Dd);
+                        Aa = fadd(Aa, w);
+                        T = test_T;
+                        last = __float_as_uint(g0.z);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    // a bulk copy still in flight targets this CTA's shared memory: observe every issued stage before the warp may exit
+    for (int s = waited; s < issued; s++) mbar_wait(&bk.mbar[s & 1], (uint32_t)(s >> 1) & 1u);
+    if (inside) {
+        if (T != 0.0f) T_out = T;
+        const size_t HW = (size_t)a.H * a.W;
+        const size_t pix = (size_t)py * a.W + px;
+        a.final_T[v * HW + pix] = T_out;
+        a.n_contrib[v * HW + pix] = last;
+        float *oc = a.out_color + (size_t)v * 3 * HW;
+        oc[pix] = ffma(T_out, a.bg[0], C0);
+        oc[HW + pix] = ffma(T_out, a.bg[1], C1);
+        oc[2 * HW + pix] = ffma(T_out, a.bg[2], C2);
+        a.out_depth[v * HW + pix] = Dd;
+        a.out_alpha[v * HW + pix] = Aa;
+    }
+}
+#endif // FWD_BULK
 
 void launch_blend_fwd(const BlendArgs &a, cudaStream_t st)
 {
@@ -313,6 +542,72 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
         }
         __syncwarp();
         const int cnt = __popc(b);
+#if BWD_ILP2
+        // Two hits per iteration (SLAB_PACK layout).  Their power / exp / alpha evaluations and, when both contribute, their two
+        // reduction butterflies are independent instruction streams; only the short per-pixel recurrences (T, rg) are ordered.
+        if ((cnt & 1) && lane == 0) { // pad an odd count: finite centre, zero conic/opacity -> alpha = 0 -> never contributes
+            sl.rec[3 * cnt] = make_float4(0.f, 0.f, 0.f, 0.f);
+            sl.rec[3 * cnt + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
+        // per-pixel state update of one contributing hit: returns q = G * dL/dalpha and w = alpha * T
+        auto pixel_update = [&](const float4 q2, float G, float alpha, float &q, float &w) {
+            const float cg = fmaf(q2.x, gC0, fmaf(q2.y, gC1, fmaf(q2.z, gC2, fmaf(q2.w, gD, gA))));
+            const float one_m_a = 1.0f - alpha;
+            float inv;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(one_m_a));
+#if BWD_T_DIV == 2
+            T = __fdiv_rn(T, one_m_a);
+#elif BWD_T_DIV == 1
+            inv = fmaf(fmaf(-one_m_a, inv, 1.0f), inv, inv);
+            T = T * inv;
+#else
+            T = T * inv;
+#endif
+            w = alpha * T;
+            rg = fmaf(last_alpha, last_cg - rg, rg);
+            last_cg = cg;
+            last_alpha = alpha;
+            q = G * fmaf(T, cg - rg, -(Kbg * inv));
+        };
+        auto reduce_add = [&](float e, uint32_t rid) {
+#if SGRAD_F64
+            if (slot >= 0) atomicAdd(sg_slot + GS_SGRAD_F64_DOUBLES * (size_t)rid, (double)e);
+#else
+            if (slot >= 0) atomicAdd(sg_slot + 12 * (size_t)rid, e);
+#endif
+        };
+        for (int i = 0; i < cnt; i += 2) {
+            const float4 g0a = sl.rec[3 * i], q1a = sl.rec[3 * i + 1];
+            const float4 g0b = sl.rec[3 * i + 3], q1b = sl.rec[3 * i + 4];
+            const float dxa = fsub(g0a.x, fpx), dya = fsub(g0a.y, fpy), dxb = fsub(g0b.x, fpx), dyb = fsub(g0b.y, fpy);
+            const float pa = power_prescaled(q1a.x, q1a.y, q1a.z, dxa, dya), pb = power_prescaled(q1b.x, q1b.y, q1b.z, dxb, dyb);
+            const float Ga = gs_exp(pa), Gb = gs_exp(pb);
+            const float aa = fminf(GS_ALPHA_MAX, fmul(q1a.w, Ga)), ab = fminf(GS_ALPHA_MAX, fmul(q1b.w, Gb));
+            const bool ca = ((int)__float_as_uint(g0a.z) < last) && !(pa > 0.0f) && !(aa < GS_ALPHA_MIN);
+            const bool cb = ((int)__float_as_uint(g0b.z) < last) && !(pb > 0.0f) && !(ab < GS_ALPHA_MIN);
+            const bool any_a = __any_sync(FULL, ca), any_b = __any_sync(FULL, cb);
+            if (!any_a && !any_b) continue;
+            float qa = 0.f, wa = 0.f, qb = 0.f, wb = 0.f;
+            if (ca) pixel_update(sl.rec[3 * i + 2], Ga, aa, qa, wa);
+            if (cb) pixel_update(sl.rec[3 * i + 5], Gb, ab, qb, wb);
+            if (any_a && any_b) { // the common case: two independent butterflies, interleaved by the scheduler
+                const float qxa = qa * dxa, qya = qa * dya, qxb = qb * dxb, qyb = qb * dyb;
+                const float ea = butterfly10(qa, qxa, qya, qxa * dxa, qxa * dya, qya * dya, wa * gC0, wa * gC1, wa * gC2, wa * gD, lane);
+                const float eb = butterfly10(qb, qxb, qyb, qxb * dxb, qxb * dyb, qyb * dyb, wb * gC0, wb * gC1, wb * gC2, wb * gD, lane);
+                reduce_add(ea, __float_as_uint(g0a.w));
+                reduce_add(eb, __float_as_uint(g0b.w));
+            } else if (any_a) {
+                const float qxa = qa * dxa, qya = qa * dya;
+                reduce_add(butterfly10(qa, qxa, qya, qxa * dxa, qxa * dya, qya * dya, wa * gC0, wa * gC1, wa * gC2, wa * gD, lane),
+                           __float_as_uint(g0a.w));
+            } else {
+                const float qxb = qb * dxb, qyb = qb * dyb;
+                reduce_add(butterfly10(qb, qxb, qyb, qxb * dxb, qxb * dyb, qyb * dyb, wb * gC0, wb * gC1, wb * gC2, wb * gD, lane),
+                           __float_as_uint(g0b.w));
+            }
+        }
+#else
         for (int i = 0; i < cnt; i++) {
             const float4 g0 = sl.rec[3 * i], q1 = sl.rec[3 * i + 1];
 #if SLAB_PACK
@@ -360,6 +655,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, BWD_MIN_BLOCKS) blend_bwd_
             if (slot >= 0) atomicAdd(sg_slot + 12 * (size_t)rid, e);
 #endif
         }
+#endif
         __syncwarp();
     }
 }

@@ -81,7 +81,7 @@ int launch_depth_order(const uint32_t *tiles_touched, uint32_t *offsets_sorted, 
                        const BinLayout &L, const uint32_t **order_sorted, const uint64_t **total_dev, cudaStream_t st, int *n_launches);
 #define B200GS_MAX_INSTANCES_I64 ((int64_t)0x7fffffff) // (Gaussian, tile) instances per call: 32-bit indices with headroom
 int launch_binning(const uint32_t *order_sorted, const uint2 *rects, const uint32_t *offsets_sorted, int P, int V, int grid_x, int grid_y,
-                   int64_t D, char *bin_base, const BinLayout &L, cudaStream_t st, int *n_launches);
+                   int64_t D, const uint64_t *D_dev, char *bin_base, const BinLayout &L, cudaStream_t st, int *n_launches);
 int launch_test_sort32(uint32_t *ka, uint32_t *kb, uint32_t *va, uint32_t *vb, int64_t n, int nbits, char *scratch, size_t scratch_bytes,
                        int *result_in_b, cudaStream_t st);
 size_t test_sort32_scratch_bytes(int64_t n);

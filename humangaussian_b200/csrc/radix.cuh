@@ -29,9 +29,12 @@ __device__ __forceinline__ uint32_t digit_of(KeyT k, int shift, int bits)
 
 // counts[d][cta] = number of items of CTA `cta` whose digit is d          (digit-major: the scan is contiguous)
 template <typename KeyT, int RADIX_BITS, int IPT>
-__global__ void __launch_bounds__(THREADS) count_kernel(const KeyT *__restrict__ keys, int64_t n, int shift, int bits,
+__global__ void __launch_bounds__(THREADS) count_kernel(const KeyT *__restrict__ keys, int64_t n, const uint64_t *__restrict__ n_dev, int shift, int bits,
                                                          uint32_t *__restrict__ counts, uint32_t nblocks)
 {
+    // n_dev (optional): the item count lives on the device (the host sized the grid for the capacity `n` without waiting for
+    // it); CTAs past the real count write zero counts and do nothing else
+    if (n_dev) n = min(n, (int64_t)*n_dev);
     constexpr int BINS = 1 << RADIX_BITS;
     constexpr int TILE = THREADS * IPT;
     __shared__ uint32_t sh[BINS];
@@ -88,9 +91,12 @@ __global__ void __launch_bounds__(THREADS) scan_counts_kernel(uint32_t *__restri
 template <typename KeyT, int RADIX_BITS, int IPT>
 __global__ void __launch_bounds__(THREADS) scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
                                                            const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out,
-                                                           int64_t n, int shift, int bits, const uint32_t *__restrict__ counts /* scanned */,
-                                                           uint32_t nblocks, const uint32_t *__restrict__ totals)
+                                                           int64_t n, const uint64_t *__restrict__ n_dev, int shift, int bits,
+                                                           const uint32_t *__restrict__ counts /* scanned */, uint32_t nblocks,
+                                                           const uint32_t *__restrict__ totals)
 {
+    if (n_dev) n = min(n, (int64_t)*n_dev);
+    if ((int64_t)blockIdx.x * (THREADS * IPT) >= n) return; // a CTA past the device-side count (whole CTA: no barrier is skipped)
     constexpr int BINS = 1 << RADIX_BITS;
     constexpr int TILE = THREADS * IPT;
     constexpr int DPT = (BINS + THREADS - 1) / THREADS; // digits per thread in the per-digit phases
