@@ -54,6 +54,7 @@ BinLayout binning_layout(int64_t capacity, int ntiles_total, int64_t n_vp)
     L.order = o; o += gs_align(nvp * 4);
     L.tile_order = o; o += gs_align((size_t)ntiles_total * 4);
     L.tile_order_cnt = o; o += gs_align(64 * 4);
+    L.total_slot = o; o += 256; // the scan's exact 64-bit instance count: read by the later kernels, so NOT inside the re-used temp area
     const size_t s_depth = sort_scratch_bytes((int64_t)nvp, D_TILE, 1 << D_BITS);
     const size_t s_tile = sort_scratch_bytes((int64_t)cap, T_TILE, 1 << T_BITS);
     const size_t s_scan = gs_align(((nvp + SCAN_TILE - 1) / SCAN_TILE + 1) * 8) + 256;
@@ -112,8 +113,8 @@ int launch_depth_order(const uint32_t *tiles_touched, uint32_t *offsets_sorted, 
     char *scr = bin_base + L.temp;
     cudaMemsetAsync(scr, 0, gs_align((nblocks + 1) * 8) + 256, st);
     scan_tiles_kernel<<<(unsigned)nblocks, THREADS, 0, st>>>(vs, tiles_touched, offsets_sorted, n_vp, (volatile uint64_t *)(scr + 256),
-                                                            (uint32_t *)scr, (uint64_t *)(scr + 8));
-    *total_dev = (const uint64_t *)(scr + 8);
+                                                            (uint32_t *)scr, (uint64_t *)(bin_base + L.total_slot));
+    *total_dev = (const uint64_t *)(bin_base + L.total_slot);
     *n_launches += 1;
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
 }

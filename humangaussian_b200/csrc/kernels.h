@@ -73,6 +73,7 @@ struct BinLayout {
     size_t keys_in, keys_out, vals_in, vals_out, ranges; // per-instance tile keys (u32) / record indices (u32), tile ranges
     size_t dkeys_in, dkeys_out, order_in, order;         // per-Gaussian depth keys (u32) and the depth order (u32)
     size_t tile_order, tile_order_cnt;                   // launch order of the tiles (longest list first) + 32 bucket counters
+    size_t total_slot;                                   // u64: exact instance count of the batch (written by the tile scan)
     size_t temp, total;
     size_t temp_bytes;
 };
