@@ -42,6 +42,7 @@ struct StageTimer {
     }
 };
 
+#define B200GS_DEFERRED_MAX_NVP ((int64_t)4 << 20) // (view, Gaussian) pairs up to which the forward does not wait for its instance count
 // one pinned 8-byte word + event per (host thread, device): where the forward's instance count lands without a host wait
 struct HostSlot { unsigned long long *total; cudaEvent_t ev; };
 static HostSlot *host_slot()
@@ -151,20 +152,35 @@ int b200gs_forward(const b200gs_params *prm, const float *means3D, const float *
             StageTimer t(B200GS_STAGE_SCAN, st);
             if (launch_depth_order(a.tiles_touched, offsets, n_vp, V, bb, BL, &order_sorted, &total_dev, st, &nl)) return cuda_fail(cudaGetLastError(), "depth order");
         }
-        // The EXACT 64-bit instance count travels to a pinned host word asynchronously; the host does NOT wait for it here.
-        // Emit / tile sort / ranges / blend are enqueued sized for the caller's capacity and read the count on the device, so
-        // the GPU never idles behind a host round trip (upstream blocks on this read-back in the middle of every forward).
-        // The count is checked after the last launch, when the copy has long completed: a batch that did not fit produced
-        // clamped, in-bounds garbage and the call reports it (B200GS_E_BIN_TOO_SMALL / _E_INSTANCES) before anything is used.
+        // The EXACT 64-bit instance count travels to a pinned host word (nothing reads the possibly wrapped 32-bit offsets
+        // before it has been checked).
         HostSlot *hs = host_slot();
         if (!hs) return cuda_fail(cudaGetLastError(), "pinned count slot");
         CK(cudaMemcpyAsync(hs->total, total_dev, 8, cudaMemcpyDeviceToHost, st), "D2H num_rendered");
-        CK(cudaEventRecord(hs->ev, st), "event after count copy");
-        pending = hs;
-        const int64_t cap = instance_capacity < B200GS_MAX_INSTANCES ? instance_capacity : (int64_t)B200GS_MAX_INSTANCES;
-        if (cap > 0) {
+        int64_t cap = instance_capacity < B200GS_MAX_INSTANCES ? instance_capacity : (int64_t)B200GS_MAX_INSTANCES;
+        if (cap < 1) cap = 1; // the layout always has room for one instance
+        if (n_vp <= B200GS_DEFERRED_MAX_NVP) {
+            // Small batches (the per-view drop-in pattern, the 8-view SDS batch): the host does NOT wait here.  Emit / tile
+            // sort / ranges / blend are enqueued sized for the caller's capacity and read the count on the device, so the GPU
+            // never idles behind a host round trip (upstream blocks on this read-back in the middle of every forward).  The
+            // count is checked after the last launch, when the copy has long completed: a batch that did not fit produced
+            // clamped, in-bounds garbage and the call reports it (B200GS_E_BIN_TOO_SMALL / _E_INSTANCES) before anything is used.
+            CK(cudaEventRecord(hs->ev, st), "event after count copy");
+            pending = hs;
             StageTimer t(B200GS_STAGE_BINNING, st);
             const int brc = launch_binning(order_sorted, a.rects, offsets, P, V, gx, gy, cap, total_dev, bb, BL, st, &nl);
+            if (brc == -3) return B200GS_E_RANGE;
+            if (brc) return cuda_fail(cudaGetLastError(), "binning");
+        } else {
+            // Large batches: one wait per tens of milliseconds of work costs nothing, and launches sized for the exact count
+            // are 13 % cheaper than capacity-sized ones (measured on the 64-view step: binning 1.90 vs 2.15 ms).
+            CK(cudaStreamSynchronize(st), "sync after scan");
+            const uint64_t total = *hs->total;
+            *num_rendered = (int64_t)total;
+            if (total > (uint64_t)B200GS_MAX_INSTANCES) return B200GS_E_INSTANCES;
+            if ((int64_t)total > instance_capacity) return B200GS_E_BIN_TOO_SMALL;
+            StageTimer t(B200GS_STAGE_BINNING, st);
+            const int brc = launch_binning(order_sorted, a.rects, offsets, P, V, gx, gy, (int64_t)total, nullptr, bb, BL, st, &nl);
             if (brc == -3) return B200GS_E_RANGE;
             if (brc) return cuda_fail(cudaGetLastError(), "binning");
         }
@@ -178,7 +194,7 @@ int b200gs_forward(const b200gs_params *prm, const float *means3D, const float *
     b.final_T = (float *)(ib + IL.final_T); b.n_contrib = (uint32_t *)(ib + IL.n_contrib);
     b.out_color = out_color; b.out_depth = out_depth; b.out_alpha = out_alpha;
     (void)HW;
-    if (!pending || instance_capacity > 0) {
+    {
         StageTimer t(B200GS_STAGE_BLEND_FWD, st);
         launch_blend_fwd(b, st);
         g_launches += 1;

@@ -254,7 +254,7 @@ int launch_binning(const uint32_t *order_sorted, const uint2 *rects, const uint3
     cudaMemsetAsync(ranges, 0, (size_t)ntiles * V * 8, st);
     uint32_t *tile_order = (uint32_t *)(bin_base + L.tile_order), *tcnt = (uint32_t *)(bin_base + L.tile_order_cnt);
     const int nt_all = ntiles * V;
-    if (D == 0) { // every list is empty: identity order
+    if (D == 0 && !D_dev) { // every list is empty (count known on the host): identity order
         cudaMemsetAsync(tcnt, 0, 64 * 4, st);
         tile_bucket_count_kernel<<<(nt_all + 255) / 256, 256, 0, st>>>(ranges, nt_all, tcnt);
         tile_bucket_scatter_kernel<<<(nt_all + 255) / 256, 256, 0, st>>>(ranges, nt_all, tcnt, tile_order);

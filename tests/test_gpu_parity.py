@@ -84,7 +84,8 @@ def _check_forward_state(inp, o_out, o_st):
     assert np.array_equal(f(alpha[0].cpu().numpy()), f(alp)), "alpha image not bit-identical"
 
 
-def _check_backward(inp, o_out, gimg, o_grads, keys=("means3D", "opacities", "shs", "scales", "rotations"), extra=None):
+def _check_backward(inp, o_out, gimg, o_grads, keys=("means3D", "opacities", "shs", "scales", "rotations"), extra=None, criterion=None):
+    criterion = criterion or {}
     from humangaussian_b200.rasterizer import GaussianRasterizer
     t = _gpu_inputs(inp, keys, extra)
     P = inp["means3D"].shape[0]
@@ -97,9 +98,9 @@ def _check_backward(inp, o_out, gimg, o_grads, keys=("means3D", "opacities", "sh
     names = {"means3D": "means3D", "opacities": "opacities", "shs": "shs", "scales": "scales", "rotations": "rotations",
              "colors_precomp": "colors_precomp", "cov3D_precomp": "cov3D_precomp"}
     for k in t:
-        ok, msg = grads_agree(t[k].grad.cpu().numpy().reshape(o_grads[names[k]].shape), o_grads[names[k]])
+        ok, msg = grads_agree(t[k].grad.cpu().numpy().reshape(o_grads[names[k]].shape), o_grads[names[k]], **criterion)
         assert ok, f"dL/d{k}: {msg}"
-    ok, msg = grads_agree(m2d.grad.cpu().numpy(), o_grads["means2D"])
+    ok, msg = grads_agree(m2d.grad.cpu().numpy(), o_grads["means2D"], **criterion)
     assert ok, f"dL/dmeans2D: {msg}"
 
 
