@@ -25,7 +25,21 @@ class PipelineParams:
     debug = False
 
 
-def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_color=None):
+def _raw_tensors(pc):
+    """(opacity, scaling, rotation, f_dc, f_rest) raw parameters of the reference's GaussianModel (`_opacity`, ...:
+    gaussian_model.py:44-59) or of scene.GaussianParams (`opacity`, ...); None if `pc` exposes neither."""
+    for names in (("_opacity", "_scaling", "_rotation", "_features_dc", "_features_rest"),
+                  ("opacity", "scaling", "rotation", "features_dc", "features_rest")):
+        if all(hasattr(pc, n) for n in names):
+            return tuple(getattr(pc, n) for n in names)
+    return None
+
+
+def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_color=None, fused_activations=False):
+    """fused_activations=True (optional fast path): instead of calling the getters (sigmoid / exp /
+    F.normalize: three kernels + autograd nodes per view, gaussian_model.py:95-118) the raw parameter tensors go straight
+    to the rasteriser, which applies the activations and their Jacobians inside its kernels.  Same dict, same gradients
+    (they arrive at the raw tensors directly)."""
     xyz = pc.get_xyz
     screenspace_points = torch.zeros_like(xyz, dtype=xyz.dtype, requires_grad=True, device=xyz.device) + 0
     try:
@@ -44,6 +58,17 @@ def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_
         shs = pc.get_features
     else:
         colors = override_color
+    raw = _raw_tensors(pc) if fused_activations else None
+    if raw is not None:
+        op, sc, rot = raw[0], raw[1], raw[2]
+        image, radii, depth, alpha = rasterize_views(
+            means3D=xyz, opacities=op, viewmatrices=viewpoint_camera.world_view_transform[None], projmatrices=viewpoint_camera.full_proj_transform[None],
+            camposs=viewpoint_camera.camera_center[None], tanfovx=[settings.tanfovx], tanfovy=[settings.tanfovy], image_height=settings.image_height,
+            image_width=settings.image_width, bg=bg_color, sh_degree=pc.active_sh_degree, shs=shs, colors_precomp=colors, scales=sc, rotations=rot,
+            means2D=screenspace_points[None], scale_modifier=scaling_modifier, raw=True)
+        image, radii, depth, alpha = image[0], radii[0], depth[0], alpha[0]
+        return {"render": image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii,
+                "depth_3dgs": depth, "alpha_3dgs": alpha}
     image, radii, depth, alpha = rasterizer(means3D=xyz, means2D=screenspace_points, shs=shs, colors_precomp=colors,
                                             opacities=pc.get_opacity, scales=pc.get_scaling, rotations=pc.get_rotation,
                                             cov3D_precomp=None)

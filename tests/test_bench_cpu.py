@@ -32,3 +32,25 @@ def test_clock_sampler_degrades_without_nvidia_smi(monkeypatch):
     s.begin(); s.end()
     c = s.stop()
     assert c["samples"] == 0 and c["sm_mhz"] is None and c["reasons"] == []
+
+
+def test_roofline_accounting_and_strong_scaling_config():
+    """The algorithmic-bytes table and the strong-scaling config block, without a GPU."""
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    args = argparse.Namespace(gaussians=300000, views=64, res=1024, sh_degree=3, scene="sample")
+    P, K, HW, V, n_vis, D = 300000, 16, 1024, 64, 18_860_897, 69_468_138
+    stages = {"preprocess_fwd": (2.8, 5), "scan": (4.5, 5), "binning": (9.6, 5), "blend_fwd": (39.2, 5), "blend_bwd": (81.1, 5),
+              "preprocess_bwd": (5.1, 5)}
+    r = bench.roofline(args, stages, 143.4, 28.68, 5, P, K, HW, V, n_vis, D)
+    assert r["kernel"] == "blend_bwd" and r["bound"] == "fp32_issue" and r["unit"] == "GB/s"
+    want = V * HW * HW * 28 + D * 44 + n_vis * 40
+    assert r["algorithmic_bytes_per_launch"] == want and abs(r["achieved"] - want / (81.1 / 5 * 1e-3) / 1e9) < 1e-6
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and 0 < r["frac"] < 1
+    assert r["issue_active_pct"] and r["traffic"] == int(json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["blend_bwd"]["dram_bytes_per_view"] * V)
+    assert set(r["stages"]) == set(stages) and abs(sum(s["share_of_step"] for s in r["stages"].values()) - 142.3 / 143.4) < 1e-9
+    c8 = bench.workload_config(args, 8)
+    assert c8["views_per_gpu"] == 8 and "strong scaling" in c8["parallelism"] and c8["views_per_step"] == 64
+    assert bench.workload_config(args, 1)["parallelism"] == "single GPU"
+    assert bench.percentiles([3.0, 1.0, 2.0, 10.0])["median"] == 2.5

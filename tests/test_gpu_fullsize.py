@@ -126,3 +126,36 @@ def test_cuda_backward_vs_float64_autograd():
             assert ok, f"deg {deg}: dL/d{k} CUDA vs float64 autograd: {msg}"
         ok, msg = grads_agree(m2g.grad.cpu().numpy(), m2d.grad.numpy(), atol=1e-4, rtol=1e-3)
         assert ok, f"deg {deg}: dL/dmeans2D CUDA vs float64 autograd: {msg}"
+
+
+def test_config5_animation_frames_full_sample_ply_1024():
+    """BASELINE config 5 at its real size: content/sample.ply through the animation convention (gs_renderer.py:576-581;
+    531 327 Gaussians), per-frame positions through the frame-batched entry, 1024x1024, MiniCam orbit (animation.py:993-1004:
+    azimuth = frame index, fovy 50, radius 2): every uint8 frame equals the oracle's forward image after
+    clamp(0,1) (gs_renderer.py:1017) and (x*255).astype(uint8) (animation.py:1011)."""
+    from humangaussian_b200.animation import render_frames
+    from humangaussian_b200.cameras import MiniCamC2W, orbit_c2w
+    from humangaussian_b200.scene import sample_ply_scene
+    from oracle.gs_oracle import Oracle
+    p = sample_ply_scene(convention="animation")
+    H = W = 1024
+    fovy = math.radians(50.0)
+    yup = np.eye(4, dtype=np.float32)[[0, 2, 1, 3]]
+    frames_ids = (0, 77)
+    cams = [MiniCamC2W(yup @ orbit_c2w(0.0, float(i), 2.0).numpy(), W, H, fovy, fovy, 0.01, 100.0, device=DEV) for i in frames_ids]
+    g = torch.Generator().manual_seed(0)
+    xyz = torch.stack([p.xyz, p.xyz + 0.002 * torch.randn(p.P, 3, generator=g)]).to(DEV)   # frame 1: displaced positions
+    pd = p.to(DEV)
+    frames = render_frames(pd, xyz, cams, torch.zeros(3, device=DEV)).cpu().numpy()
+    assert frames.shape == (2, H, W, 3) and frames.dtype == np.uint8
+    with torch.no_grad():
+        base = dict(opacities=p.get_opacity.numpy(), shs=p.get_features.contiguous().numpy(), scales=p.get_scaling.numpy(),
+                    rotations=p.get_rotation.numpy(), sh_degree=0, bg=np.zeros(3, np.float32), image_height=H, image_width=W,
+                    tanfovx=math.tan(fovy * 0.5), tanfovy=math.tan(fovy * 0.5))
+    for f, cam in enumerate(cams):
+        o = Oracle()
+        col, rad, dep, alp = o.forward(means3D=xyz[f].cpu().numpy(), viewmatrix=cam.world_view_transform.cpu().numpy(),
+                                       projmatrix=cam.full_proj_transform.cpu().numpy(), campos=cam.camera_center.cpu().numpy(), **base)
+        assert o.state()["num_rendered"] > 1000000
+        want = (np.clip(col, 0.0, 1.0).transpose(1, 2, 0) * np.float32(255.0)).astype(np.uint8)
+        assert np.array_equal(frames[f], want), f"frame {f}: {(frames[f] != want).sum()} bytes differ"

@@ -380,3 +380,33 @@ def test_fused_raw_activations_match_torch_activations_and_autograd(deg):
     for (o, m, shape), g in zip(fields, ref):
         ok, msg = grads_agree(flat.grad.narrow(0, o, m).view(shape).cpu().numpy().reshape(P, -1), g.cpu().numpy().reshape(P, -1))
         assert ok, f"packed raw gradient field at {o}: {msg}"
+
+
+def test_render_fused_activation_option_matches_the_getter_path():
+    """renderer.render(fused_activations=True): raw tensors into the kernels instead of the getters' torch kernels; same
+    dict, images to tolerance, gradients at the raw tensors by the gradient criterion (incl. the means2D sink)."""
+    from humangaussian_b200.cameras import Camera, orbit_c2w
+    from humangaussian_b200.renderer import PipelineParams, render
+    from humangaussian_b200.scene import synthetic_body
+    cam = Camera(orbit_c2w(10, 30, 1.8), math.radians(60), 96, 128, device=DEV)
+    outs = []
+    for fused in (False, True):
+        p = synthetic_body(4000, sh_degree=2, seed=5)
+        p.scaling += math.log(5.0)
+        p = p.to(DEV)
+        leaves = (p.xyz, p.features_dc, p.features_rest, p.scaling, p.rotation, p.opacity)
+        for t in leaves:
+            t.requires_grad_(True)
+        out = render(cam, p, PipelineParams(), torch.tensor([0.2, 0.1, 0.3], device=DEV), fused_activations=fused)
+        (out["render"].square().sum() + out["depth_3dgs"].sum() + out["alpha_3dgs"].sum()).backward()
+        outs.append((out, [t.grad for t in leaves]))
+    (a, ga), (b, gb) = outs
+    assert set(a) == set(b) and torch.equal(a["radii"], b["radii"])
+    for k in ("render", "depth_3dgs", "alpha_3dgs"):
+        ok, worst = close(b[k].detach().cpu().numpy(), a[k].detach().cpu().numpy())
+        assert ok, (k, worst)
+    for x, y in zip(ga, gb):
+        ok, msg = grads_agree(y.cpu().numpy().reshape(4000, -1), x.cpu().numpy().reshape(4000, -1))
+        assert ok, msg
+    ok, msg = grads_agree(b["viewspace_points"].grad.cpu().numpy(), a["viewspace_points"].grad.cpu().numpy())
+    assert ok, msg

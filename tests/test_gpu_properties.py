@@ -308,3 +308,29 @@ def test_view_batch_is_halved_when_the_instance_limit_is_hit(monkeypatch):
     for x, y in zip(g_full, g_split):
         ok, msg = grads_agree(y.cpu().numpy().reshape(-1, x.shape[-1]), x.cpu().numpy().reshape(-1, x.shape[-1]), atol=1e-4, rtol=1e-3)
         assert ok, msg
+
+
+def test_large_batch_path_equals_per_view_calls():
+    """More than 4 M (view, Gaussian) pairs take the forward's in-place wait for the instance count (exact-size launches);
+    fewer take the deferred check (capacity-size launches).  Both must give the same images and state: 16 views x 300 k
+    Gaussians in one call (first path) against 16 single-view calls (second path), bit for bit."""
+    from humangaussian_b200 import rasterizer as R
+    from humangaussian_b200.cameras import sample_orbit_cameras
+    from humangaussian_b200.renderer import stack_cameras
+    from humangaussian_b200.scene import synthetic_body
+    P, V, HW = 300_000, 16, 256
+    p = synthetic_body(P, sh_degree=1, seed=3).to(DEV)
+    cams = sample_orbit_cameras(V, HW, HW, seed=9, device=DEV)
+    vm, pm, cp, tanx, tany = stack_cameras(cams, DEV)
+    with torch.no_grad():
+        kw = dict(means3D=p.get_xyz, opacities=p.get_opacity, shs=p.get_features.contiguous(), scales=p.get_scaling, rotations=p.get_rotation,
+                  image_height=HW, image_width=HW, bg=torch.zeros(3, device=DEV), sh_degree=1)
+        cb, rb, db, ab = R.rasterize_views(viewmatrices=vm, projmatrices=pm, camposs=cp, tanfovx=tanx, tanfovy=tany, **kw)
+        total = R.last_num_rendered()
+        n = 0
+        for v in range(V):
+            c, r, d, a = R.rasterize_views(viewmatrices=vm[v:v + 1], projmatrices=pm[v:v + 1], camposs=cp[v:v + 1], tanfovx=tanx[v:v + 1],
+                                           tanfovy=tany[v:v + 1], **kw)
+            n += R.last_num_rendered()
+            assert torch.equal(c[0], cb[v]) and torch.equal(r[0], rb[v]) and torch.equal(d[0], db[v]) and torch.equal(a[0], ab[v])
+    assert n == total and total > 0
