@@ -65,6 +65,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip per_view / views8 / cuda_baseline / weak_scaling")
     ap.add_argument("--stage-json", default=None, help="also write the per-stage timing table to this file")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="(internal) with --impl reference: time this many views once, plus the torch CPU paths, and print the "
+                         "`cpu_baseline` object -- the GPU arm runs its CPU baseline in such a child process so that the pinned "
+                         "OpenMP pool never shares a process (or a core binding) with the ranks that drive GPUs")
     return ap.parse_args()
 
 
@@ -226,10 +230,26 @@ def torch_cpu_paths(args, p=None):
                 "torch_threads": torch.get_num_threads()}
 
 
+def cpu_sample(args):
+    """child-process mode of the GPU arm's `cpu_baseline` (see --cpu-sample)"""
+    p = load_scene(args)
+    a = _oracle_inputs(args, p)
+    oracle_views_per_s(args, 1, a)  # warm the pool
+    nv = args.cpu_sample
+    v, dt = oracle_views_per_s(args, nv, a)
+    emit({"value": v, "unit": "views/s", "cores": os.cpu_count(), "threads_used": os.cpu_count(), "kind": "port",
+          "omp": {k: os.environ.get(k) for k in ("OMP_PROC_BIND", "OMP_PLACES", "OMP_WAIT_POLICY")},
+          "sample": f"{nv} of the {args.views} views of this workload, full fwd+bwd by oracle/gs_oracle.c in a child process (one pinned OpenMP "
+                    f"pool, all host threads; torch's pool parked), {dt:.1f} s",
+          "torch_cpu_paths": torch_cpu_paths(args, p)})
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.cpu_sample:
+        return cpu_sample(args)
     cores = os.cpu_count()
     t_all = time.perf_counter()
     a = _oracle_inputs(args)
@@ -573,15 +593,19 @@ def run_b200(args):
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        nv = 2
-        a = _oracle_inputs(args, h.params)
-        oracle_views_per_s(args, 1, a)  # warm the pool
-        v, dt = oracle_views_per_s(args, nv, a)
-        cpu = {"value": v, "unit": "views/s", "cores": os.cpu_count(), "threads_used": os.cpu_count(), "kind": "port",
-               "omp": {k: os.environ.get(k) for k in ("OMP_PROC_BIND", "OMP_PLACES", "OMP_WAIT_POLICY")},
-               "sample": f"{nv} of the {args.views} views of this workload, full fwd+bwd by oracle/gs_oracle.c (one pinned OpenMP pool, all host "
-                         f"threads; torch's pool parked), {dt:.1f} s",
-               "torch_cpu_paths": torch_cpu_paths(args, h.params)}
+        # in a child process: the oracle's OpenMP pool is pinned (OMP_PROC_BIND), and a pinned pool inside a process that
+        # drives a GPU binds that process's main thread to core 0 -- with 8 ranks doing it the launches of all GPUs
+        # time-share one core (measured: 35.9 ms instead of 3.9 ms per 8-view step)
+        env = dict(os.environ)
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--cpu-sample", "2", "--views", str(args.views),
+               "--gaussians", str(args.gaussians), "--res", str(args.res), "--sh-degree", str(args.sh_degree), "--scene", args.scene]
+        try:
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+            cpu = json.loads([l for l in out.stdout.splitlines() if l.strip()][-1])
+        except Exception as e:  # the GPU line must not die with its CPU baseline
+            cpu = {"error": f"cpu baseline child failed: {e!r}"}
 
     if rank == 0:
         line = {"impl": args.impl, "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world,
@@ -768,11 +792,13 @@ def emit(line: dict):
 
 def main():
     global _JSON_FD
-    # one pinned OpenMP pool for the CPU arm: must be in the environment before libgomp initialises (numpy / torch import)
-    os.environ.setdefault("OMP_PROC_BIND", "close")
-    os.environ.setdefault("OMP_PLACES", "cores")
-    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
     args = parse()
+    if args.impl == "reference":
+        # one pinned OpenMP pool for the CPU arm: must be in the environment before libgomp initialises (numpy / torch
+        # import).  ONLY in the CPU arm's own process: binding also pins the process's main thread (see run_b200).
+        os.environ.setdefault("OMP_PROC_BIND", "close")
+        os.environ.setdefault("OMP_PLACES", "cores")
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")
     sys.stdout.flush()
     _JSON_FD = os.dup(1)
     os.dup2(2, 1)  # C-level writers to stdout (e.g. "NCCL version ...") must not pollute the one-line contract

@@ -55,36 +55,47 @@ __global__ void __launch_bounds__(THREADS) count_kernel(const KeyT *__restrict__
     for (int i = threadIdx.x; i < BINS; i += THREADS) counts[(size_t)i * nblocks + blockIdx.x] = sh[i];
 }
 
-// one CTA per digit: exclusive scan of its row of per-CTA counts in place; totals[d] = row sum
+// one CTA per digit: exclusive scan of its row of per-CTA counts in place; totals[d] = row sum.
+// The row is walked in slabs of 4 * THREADS consecutive counts (four per thread: neighbouring lanes touch neighbouring
+// 16-byte groups) with one block scan per slab and a running carry.  (Round 1 gave every thread one contiguous chunk of the
+// row: lane-to-lane stride of `nblocks / 256` words, 47 us per launch on the 64-view step, six launches per step.)
 __global__ void __launch_bounds__(THREADS) scan_counts_kernel(uint32_t *__restrict__ counts, uint32_t nblocks, uint32_t *__restrict__ totals)
 {
-    __shared__ uint32_t s_wsum[WARPS];
+    __shared__ uint32_t s_wsum[2][WARPS];
     uint32_t *row = counts + (size_t)blockIdx.x * nblocks;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t per = (nblocks + THREADS - 1) / THREADS;
-    const uint32_t b0 = min(nblocks, (uint32_t)tid * per), b1 = min(nblocks, b0 + per);
-    uint32_t tsum = 0;
-    for (uint32_t b = b0; b < b1; b++) tsum += row[b];
-    uint32_t incl = tsum;
+    uint32_t carry = 0;
+    int buf = 0;
+    for (uint32_t base = 0; base < nblocks; base += 4 * THREADS, buf ^= 1) {
+        const uint32_t i0 = base + 4 * (uint32_t)tid;
+        uint32_t c[4];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
+        for (int j = 0; j < 4; j++) c[j] = (i0 + j < nblocks) ? row[i0 + j] : 0u;
+        const uint32_t tsum = c[0] + c[1] + c[2] + c[3];
+        uint32_t incl = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) s_wsum[buf][warp] = incl;
+        __syncthreads(); // one barrier per slab: the warp sums are double buffered
+        uint32_t wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) {
+            const uint32_t x = s_wsum[buf][w];
+            if (w < warp) wbase += x;
+            total += x;
+        }
+        uint32_t run = carry + wbase + incl - tsum;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (i0 + j < nblocks) row[i0 + j] = run;
+            run += c[j];
+        }
+        carry += total;
     }
-    if (lane == 31) s_wsum[warp] = incl;
-    __syncthreads();
-    uint32_t wbase = 0, total = 0;
-    for (int w = 0; w < WARPS; w++) {
-        if (w < warp) wbase += s_wsum[w];
-        total += s_wsum[w];
-    }
-    uint32_t run = wbase + incl - tsum;
-    for (uint32_t b = b0; b < b1; b++) {
-        const uint32_t c = row[b];
-        row[b] = run;
-        run += c;
-    }
-    if (tid == 0) totals[blockIdx.x] = total;
+    if (tid == 0) totals[blockIdx.x] = carry;
 }
 
 // ranked scatter of one CTA tile: stable inside the tile, destinations from the scanned counts
