@@ -145,13 +145,17 @@ def test_config5_animation_frames_full_sample_ply_1024():
     cams = [MiniCamC2W(yup @ orbit_c2w(0.0, float(i), 2.0).numpy(), W, H, fovy, fovy, 0.01, 100.0, device=DEV) for i in frames_ids]
     g = torch.Generator().manual_seed(0)
     xyz = torch.stack([p.xyz, p.xyz + 0.002 * torch.randn(p.P, 3, generator=g)]).to(DEV)   # frame 1: displaced positions
-    pd = p.to(DEV)
-    frames = render_frames(pd, xyz, cams, torch.zeros(3, device=DEV)).cpu().numpy()
-    assert frames.shape == (2, H, W, 3) and frames.dtype == np.uint8
+    # the activations are evaluated ONCE (host libm and the device's expf differ in the last bit) and the same values feed both
+    # sides: `pc` is anything with GaussianModel's getters
+    import types
     with torch.no_grad():
-        base = dict(opacities=p.get_opacity.numpy(), shs=p.get_features.contiguous().numpy(), scales=p.get_scaling.numpy(),
-                    rotations=p.get_rotation.numpy(), sh_degree=0, bg=np.zeros(3, np.float32), image_height=H, image_width=W,
-                    tanfovx=math.tan(fovy * 0.5), tanfovy=math.tan(fovy * 0.5))
+        act = dict(get_opacity=p.get_opacity, get_features=p.get_features.contiguous(), get_scaling=p.get_scaling, get_rotation=p.get_rotation)
+    pc = types.SimpleNamespace(active_sh_degree=0, **{k: v.to(DEV) for k, v in act.items()})
+    frames = render_frames(pc, xyz, cams, torch.zeros(3, device=DEV)).cpu().numpy()
+    assert frames.shape == (2, H, W, 3) and frames.dtype == np.uint8
+    base = dict(opacities=act["get_opacity"].numpy(), shs=act["get_features"].numpy(), scales=act["get_scaling"].numpy(),
+                rotations=act["get_rotation"].numpy(), sh_degree=0, bg=np.zeros(3, np.float32), image_height=H, image_width=W,
+                tanfovx=math.tan(fovy * 0.5), tanfovy=math.tan(fovy * 0.5))
     for f, cam in enumerate(cams):
         o = Oracle()
         col, rad, dep, alp = o.forward(means3D=xyz[f].cpu().numpy(), viewmatrix=cam.world_view_transform.cpu().numpy(),
