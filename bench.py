@@ -160,7 +160,7 @@ def _oracle_inputs(args, p=None):
                     scales=p.get_scaling.numpy(), rotations=p.get_rotation.numpy())
 
 
-def oracle_views_per_s(args, n_views, a=None, threads=None):
+def oracle_views_per_s(args, n_views, a=None, threads=None, o=None):
     """fwd+bwd of n_views views of the SAME workload by the CPU oracle.  One OpenMP pool: torch's intra-op pool is parked at one
     thread while the oracle runs, the oracle's threads are pinned (OMP_PROC_BIND=close, set in main() before libgomp loads), and
     the count is set explicitly because torchrun exports OMP_NUM_THREADS=1."""
@@ -176,7 +176,7 @@ def oracle_views_per_s(args, n_views, a=None, threads=None):
     saved = torch.get_num_threads()
     torch.set_num_threads(1)
     try:
-        o = Oracle(threads=threads)
+        o = o or Oracle(threads=threads)  # one context for all steps: its buffers are allocated (and page-faulted) once
         t0 = time.perf_counter()
         for cam in cams:
             o.forward(**a, viewmatrix=cam.world_view_transform.numpy(), projmatrix=cam.full_proj_transform.numpy(),
@@ -233,10 +233,12 @@ def torch_cpu_paths(args, p=None):
 def cpu_sample(args):
     """child-process mode of the GPU arm's `cpu_baseline` (see --cpu-sample)"""
     p = load_scene(args)
+    from oracle.gs_oracle import Oracle
     a = _oracle_inputs(args, p)
-    oracle_views_per_s(args, 1, a)  # warm the pool
+    o = Oracle(threads=os.cpu_count())
+    oracle_views_per_s(args, 1, a, o=o)  # warm the pool and the context's buffers
     nv = args.cpu_sample
-    v, dt = oracle_views_per_s(args, nv, a)
+    v, dt = oracle_views_per_s(args, nv, a, o=o)
     emit({"value": v, "unit": "views/s", "cores": os.cpu_count(), "threads_used": os.cpu_count(), "kind": "port",
           "omp": {k: os.environ.get(k) for k in ("OMP_PROC_BIND", "OMP_PLACES", "OMP_WAIT_POLICY")},
           "sample": f"{nv} of the {args.views} views of this workload, full fwd+bwd by oracle/gs_oracle.c in a child process (one pinned OpenMP "
@@ -252,12 +254,14 @@ def run_reference(args):
         return cpu_sample(args)
     cores = os.cpu_count()
     t_all = time.perf_counter()
+    from oracle.gs_oracle import Oracle
     a = _oracle_inputs(args)
+    o = Oracle(threads=cores)
     for _ in range(min(args.warmup, 1)):
-        oracle_views_per_s(args, 1, a)
+        oracle_views_per_s(args, 1, a, o=o)
     vals, dts = [], []
     for _ in range(args.steps):
-        v, dt = oracle_views_per_s(args, 1, a)  # each step = a bounded sample: 1 view of the batch, full fwd+bwd
+        v, dt = oracle_views_per_s(args, 1, a, o=o)  # each step = a bounded sample: 1 view of the batch, full fwd+bwd
         vals.append(v)
         dts.append(dt)
     value = len(vals) / sum(dts)

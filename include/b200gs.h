@@ -16,9 +16,12 @@
  *   - every `const float*` / `float*` / `int32_t*` / `void*` buffer is DEVICE memory on the current CUDA device
  *     unless the parameter comment says "host";
  *   - all kernels are enqueued on `stream` (a cudaStream_t passed as void*); functions return after enqueueing,
- *     except b200gs_forward which performs ONE stream synchronisation to read back the instance count
- *     (upstream does the same, once per view; here it is once per batch of views);
- *   - return value 0 = success, negative = b200gs_status; nothing throws across the ABI; no global state;
+ *     except b200gs_forward which reads the instance count back once per call (upstream blocks on it in the middle of
+ *     every view's forward).  For batches of up to 4 M (view, Gaussian) pairs every kernel of the forward is enqueued
+ *     FIRST (sized for instance_capacity, the count read on the device) and the host then waits on an event recorded
+ *     right after the scan -- the GPU never idles behind the host; larger batches wait once in place;
+ *   - return value 0 = success, negative = b200gs_status; nothing throws across the ABI; process state is limited to an
+ *     error string, a launch counter, the optional stage profiler and one pinned count word + event per (thread, device);
  *   - matrices are the reference's row-vector-convention 4x4 tensors read as 16 contiguous floats
  *     (world_view_transform / full_proj_transform, gaussiansplatting/scene/cameras.py:50-52).
  */
@@ -88,8 +91,10 @@ size_t b200gs_backward_scratch_bytes(int32_t P, int32_t n_views);
  *   bg [3]; viewmatrix [V,16]; projmatrix [V,16]; campos [V,3].
  * Outputs: out_color [V,3,H,W]; out_depth [V,1,H,W]; out_alpha [V,1,H,W]; radii [V,P] int32.
  * instance_capacity = the capacity binning_buf was sized for with b200gs_binning_bytes().
- * num_rendered (host, int64[1]) receives the total number of (Gaussian,tile) instances over all views;
- * if it exceeds instance_capacity the call returns B200GS_E_BIN_TOO_SMALL before binning (grow, call again).
+ * num_rendered (host, int64[1]) receives the EXACT (64-bit) number of (Gaussian,tile) instances over all views;
+ * if it exceeds instance_capacity the call returns B200GS_E_BIN_TOO_SMALL (grow, call again: the outputs of the failed
+ * call are unspecified but every access stayed inside the buffers); above B200GS_MAX_INSTANCES it returns
+ * B200GS_E_INSTANCES (render fewer views per call).
  */
 int b200gs_forward(const b200gs_params *prm,
                    const float *means3D, const float *shs, const float *colors_precomp, const float *opacities,
