@@ -145,8 +145,8 @@ def workload_config(args, n, views_per_gpu=None):
                         "raw optimiser parameters in, activations fused in the kernels",
             "gaussians": args.gaussians, "views_per_step": args.views, "views_per_gpu": vpg, "resolution": args.res,
             "sh_degree": args.sh_degree, "calling_pattern": "one batched call per step (rasterize_views_packed, raw=True)",
-            "parallelism": (f"strong scaling: the {args.views}-camera batch sharded round-robin over {n} GPUs ({vpg} views each); scene broadcast "
-                            "once; one NCCL all-reduce of the packed gradient buffer per step") if n > 1 else "single GPU",
+            "parallelism": (f"strong scaling: the {args.views}-camera batch sharded over {n} GPUs ({vpg} views each, balanced by a camera-only "
+                            "cost proxy); scene broadcast once; one NCCL all-reduce of the packed gradient buffer per step") if n > 1 else "single GPU",
             "l2_policy": "per-step working set (views x ~48 MB images/state + geometry + sort buffers, > 0.4 GB even at 8 views) >> 126 MB L2; "
                          "no explicit flush"}
 
@@ -512,8 +512,10 @@ def run_b200(args):
     h = Harness(args, dev, rank, world)
     P, HW, deg, K = h.P, h.HW, h.deg, h.K
 
-    # ---- strong scaling: the fixed batch sharded round-robin (GaussianDreamer.py:244-248's views)
-    mine = shard_views(args.views, rank, world)
+    # ---- strong scaling: the fixed batch sharded over the ranks (GaussianDreamer.py:244-248's views), equal
+    # counts, balanced by an a-priori cost from the cameras alone (dist.view_cost_proxy): the step ends at the slowest rank
+    from humangaussian_b200.dist import view_cost_proxy
+    mine = shard_views(args.views, rank, world, "balanced", [view_cost_proxy(c) for c in h.all_cams])
     cs = h.camera_set([h.all_cams[i] for i in mine], seed=rank)
     V = cs["V"]
     W = max(args.warmup, 3)

@@ -64,6 +64,31 @@ def test_sharding_partitions():
                 assert max(map(len, parts)) - min(map(len, parts)) <= 1
 
 
+def test_balanced_sharding_evens_out_the_cost():
+    import math
+    from humangaussian_b200.cameras import sample_orbit_cameras
+    cams = sample_orbit_cameras(64, 64, 64, seed=1000)
+    costs = [D.view_cost_proxy(c) for c in cams]
+    assert all(c > 0 for c in costs) and max(costs) / min(costs) > 2.0          # the training distribution spans > 2x in scale
+    for w in (1, 2, 4, 8):
+        parts = [D.shard_views(64, r, w, "balanced", costs) for r in range(w)]
+        assert sorted(sum(parts, [])) == list(range(64)) and {len(p) for p in parts} == {64 // w}
+        loads = [sum(costs[i] for i in p) for p in parts]
+        rr = [sum(costs[i] for i in D.shard_views(64, r, w)) for r in range(w)]
+        assert max(loads) / (sum(loads) / w) <= max(rr) / (sum(rr) / w) + 1e-12   # never worse than round-robin
+        assert max(loads) / (sum(loads) / w) < 1.02
+    # uneven counts, determinism, argument checking
+    parts = [D.shard_views(7, r, 3, "balanced", [5, 1, 1, 1, 4, 1, 1]) for r in range(3)]
+    assert sorted(sum(parts, [])) == list(range(7)) and sorted(map(len, parts)) == [2, 2, 3]
+    assert parts == [D.shard_views(7, r, 3, "balanced", [5, 1, 1, 1, 4, 1, 1]) for r in range(3)]
+    with pytest.raises(ValueError):
+        D.shard_views(7, 0, 3, "balanced")
+    # the proxy is the projected-area scale of the camera
+    c = cams[0]
+    d = float(c.camera_center.norm())
+    assert abs(D.view_cost_proxy(c) - 1.0 / (d * math.tan(c.FoVy / 2)) ** 2) < 1e-5  # float32 norm vs float64 sqrt
+
+
 def test_pack_unpack_roundtrip():
     P, K = 10, 16
     t = {k: torch.randn(s) for k, s in D.field_shapes(P, K).items()}
