@@ -335,7 +335,7 @@ class Harness:
         return r
 
     # -- the reference's unchanged calling pattern: one render() per camera, torch activations (GaussianDreamer.py:244-248)
-    def step_per_view(self, cs):
+    def step_per_view(self, cs, fused=False):
         torch = self.torch
         from humangaussian_b200.renderer import PipelineParams, render
         from humangaussian_b200.scene import GaussianParams
@@ -343,7 +343,7 @@ class Harness:
         pc = GaussianParams(xyz, sh[:, :1], sh[:, 1:], sc, rot, op, self.deg)
         self.flat.grad = None
         pipe = PipelineParams()
-        outs = [render(cam, pc, pipe, self.bg) for cam in cs["dev_cams"]]
+        outs = [render(cam, pc, pipe, self.bg, fused_activations=fused) for cam in cs["dev_cams"]]
         imgs = torch.stack([o["render"] for o in outs]), torch.stack([o["depth_3dgs"] for o in outs]), torch.stack([o["alpha_3dgs"] for o in outs])
         torch.autograd.backward(list(imgs), cs["gw"])
         self.stats["radii"] = torch.stack([o["radii"] for o in outs])
@@ -580,6 +580,10 @@ def run_b200(args):
                                   "launches_per_view": mp["launches"] / (n_pv * V), "steps": n_pv,
                                   "what": "render() per camera with torch activations (gaussian_renderer/__init__.py:18-104 as called at "
                                           "GaussianDreamer.py:244-248), one backward through all views"}
+            mf = h.measure(lambda: h.step_per_view(cs, fused=True), n_pv)
+            extras["per_view_fused"] = {"value": V / (mf["ms_per_step"] * 1e-3), "unit": "views/s", "ms_per_view": mf["ms_per_step"] / V, "steps": n_pv,
+                                        "what": "the same per-camera loop with render(fused_activations=True): raw tensors into the kernels, no torch "
+                                                "activation kernels or autograd nodes (SURVEY 8f-1's optional fast path behind render())"}
             # the classic-structure CUDA comparator through the identical host path, in this process
             if args.impl == "b200" and os.path.exists(classic_path):
                 with R.use_library(classic_path):
