@@ -9,7 +9,9 @@
 //     (px, py, hx, hy), tests the Gaussian's conservative alpha-support box against the warp's patch, and the
 //     warp ballots.  Hits load the rest of the record and are compacted, in order, into a per-warp shared-memory
 //     slab; the next chunk's id/box loads are already in flight while the hits are blended.
-//     Measured on the bench workload: 1.97 of 8 patches survive per instance, 14.3 of 32 lanes contribute.
+//     Measured on the bench workload (300 k subsample of sample.ply, counter build of round 2): 2.15 of 8 patches
+//     survive the box test per instance, 83 % of those visits have a contributing lane, 13.6 of 32 lanes contribute.
+//     The hits' list position and record index ride in the two slab words the support box occupied (SLAB_PACK).
 //   * Tile lists are exactly the reference's (tile/sort indices bit-identical); culling only skips pairs whose
 //     alpha is provably < 1/255, so images are unchanged.  Forward arithmetic follows the pinned order of
 //     common.cuh: images are bit-identical to the CPU oracle.
@@ -17,6 +19,8 @@
 //     (1, dx, dy, dx^2, dx*dy, dy^2) and four colour/depth weights -- reduced over the
 //     32 lanes with a 12-shuffle multi-value butterfly (not 10 x 5 shuffles), then ten lanes each issue one
 //     red.global.add.f32 into the Gaussian's 48-byte ScreenGrad record.  Upstream: ~10 atomics per PIXEL.
+//   * The compile-time switches below are the measured experiments of round 2 (DESIGN.md section 5 has the numbers): the
+//     product is SLAB_PACK=1, BWD_T_DIV=1, everything else 0.
 #include "common.cuh"
 #include "kernels.h"
 
