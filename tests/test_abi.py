@@ -131,3 +131,35 @@ def test_packed_layout_fields_are_16_byte_aligned_for_any_P():
     t = {k: torch.randn(*shape, generator=g) for k, shape in D.field_shapes(P, K).items()}
     back = D.unpack(D.pack(t), P, K)
     assert all(torch.equal(back[k], t[k]) for k in t)
+
+
+def test_state_pool_parks_and_reuses_buffer_sets():
+    """Host logic of the state-buffer pool (no GPU): sets return when their owner is collected, are handed out again for the
+    same key, and parking is bounded."""
+    import gc
+    import torch
+    from humangaussian_b200 import rasterizer as R
+    pool = R._StatePool(max_bytes=3000)
+    mk = lambda n: dict(geom=torch.empty(n, dtype=torch.uint8), image=torch.empty(n, dtype=torch.uint8))
+    assert pool.take("k") is None
+    a = mk(500)
+    pool.give("k", a)
+    assert pool.parked == 1000 and pool.take("other") is None
+    assert pool.take("k") is a and pool.parked == 0 and pool.take("k") is None
+    pool.give("k", a)
+    pool.give("k", mk(500))
+    pool.give("k", mk(600))            # 1000 + 1000 + 1200 > 3000: dropped, not parked
+    assert pool.parked == 2000 and len(pool.free["k"]) == 2
+    pool.clear()
+    assert pool.parked == 0 and pool.take("k") is None
+    # the autograd state object hands its set back when it dies (weakref.finalize, as _forward_impl wires it)
+    import weakref
+    st = R._Ctx()
+    bufs = mk(100)
+    weakref.finalize(st, pool.give, "ctx", bufs)
+    assert pool.take("ctx") is None
+    del st
+    gc.collect()
+    assert pool.take("ctx") is bufs
+    e = R.InstanceLimitError(1 << 32)
+    assert e.count == 1 << 32 and "4294967296" in str(e) and isinstance(e, RuntimeError)
