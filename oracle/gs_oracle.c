@@ -290,22 +290,65 @@ static void preprocess_one(gso_ctx *c, int i)
     c->tiles_touched[i] = (uint32_t)((x1 - x0) * (y1 - y0));
 }
 
-/* stable LSD radix sort of (u64 key, u32 value), 8-bit digits over `nbits` low bits (A.3) */
+/* stable LSD radix sort of (u64 key, u32 value), 8-bit digits over `nbits` low bits (A.3).
+ * Parallel counting sort per pass: every thread histograms a contiguous chunk, a serial prefix over (digit, thread)
+ * gives each chunk its destination of every digit, the chunks scatter in input order -- the result is the serial
+ * stable sort's, for any thread count.  Buffers ping-pong; one copy at the end if the result sits in the temporaries. */
 static void radix_sort(uint64_t *k, uint64_t *kt, uint32_t *v, uint32_t *vt, int64_t n, int nbits)
 {
+#ifdef _OPENMP
+    int nt = omp_get_max_threads();
+#else
+    int nt = 1;
+#endif
+    if (nt > 256) nt = 256;
+    if ((int64_t)nt > n / 4096 + 1) nt = (int)(n / 4096 + 1); /* small inputs: fewer chunks */
+    int64_t *cnt = (int64_t *)malloc(sizeof(int64_t) * 256 * (size_t)nt);
+    uint64_t *ki = k, *ko = kt;
+    uint32_t *vi = v, *vo = vt;
     for (int shift = 0; shift < nbits; shift += 8) {
-        int64_t cnt[257];
-        memset(cnt, 0, sizeof(cnt));
-        for (int64_t i = 0; i < n; i++) cnt[((k[i] >> shift) & 255) + 1]++;
-        for (int d = 0; d < 256; d++) cnt[d + 1] += cnt[d];
-        for (int64_t i = 0; i < n; i++) {
-            int64_t dst = cnt[(k[i] >> shift) & 255]++;
-            kt[dst] = k[i];
-            vt[dst] = v[i];
+#pragma omp parallel num_threads(nt)
+        {
+#ifdef _OPENMP
+            const int t = omp_get_thread_num();
+#else
+            const int t = 0;
+#endif
+            const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+            int64_t *h = cnt + 256 * (size_t)t;
+            memset(h, 0, sizeof(int64_t) * 256);
+            for (int64_t i = lo; i < hi; i++) h[(ki[i] >> shift) & 255]++;
         }
-        memcpy(k, kt, n * sizeof(uint64_t));
-        memcpy(v, vt, n * sizeof(uint32_t));
+        int64_t run = 0;
+        for (int d = 0; d < 256; d++)
+            for (int t = 0; t < nt; t++) {
+                const int64_t c0 = cnt[256 * (size_t)t + d];
+                cnt[256 * (size_t)t + d] = run;
+                run += c0;
+            }
+#pragma omp parallel num_threads(nt)
+        {
+#ifdef _OPENMP
+            const int t = omp_get_thread_num();
+#else
+            const int t = 0;
+#endif
+            const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+            int64_t *h = cnt + 256 * (size_t)t;
+            for (int64_t i = lo; i < hi; i++) {
+                const int64_t dst = h[(ki[i] >> shift) & 255]++;
+                ko[dst] = ki[i];
+                vo[dst] = vi[i];
+            }
+        }
+        uint64_t *tk = ki; ki = ko; ko = tk;
+        uint32_t *tv = vi; vi = vo; vo = tv;
     }
+    if (ki != k) {
+        memcpy(k, ki, (size_t)n * sizeof(uint64_t));
+        memcpy(v, vi, (size_t)n * sizeof(uint32_t));
+    }
+    free(cnt);
 }
 
 static inline float eval_power(float A, float B, float C, float dx, float dy)
@@ -471,13 +514,16 @@ int gso_backward(gso_ctx *c, const float *dL_dcolor, const float *dL_ddepth_img,
     const int P = c->P, H = c->H, W = c->W;
     const int64_t D = c->D;
     const float *bg = c->bg;
-    double *part = (double *)calloc((size_t)(D > 0 ? D : 1) * 10, sizeof(double));
+    /* every tile owns the slice [r0, r1) of `part`: it zeroes it itself (parallel first touch; a calloc of D*80 bytes
+     * followed by a serial reduction made the backward 0.7 s serial per 1024^2 view of 300 k Gaussians) */
+    double *part = (double *)malloc((size_t)(D > 0 ? D : 1) * 10 * sizeof(double));
 #pragma omp parallel for schedule(dynamic, 1)
     for (int t = 0; t < c->ntiles; t++) {
         int tx0 = (t % c->gx) * TILE, ty0 = (t / c->gx) * TILE;
         uint32_t r0 = c->ranges[2 * t], r1 = c->ranges[2 * t + 1];
         int n = (int)(r1 - r0);
         if (n == 0) continue;
+        memset(part + (size_t)r0 * 10, 0, sizeof(double) * 10 * (size_t)n);
         float *loc = (float *)malloc(sizeof(float) * 10 * n);
         for (int j = 0; j < n; j++) {
             uint32_t g = c->vals[r0 + j];
@@ -544,12 +590,26 @@ int gso_backward(gso_ctx *c, const float *dL_dcolor, const float *dL_ddepth_img,
             }
         free(loc);
     }
-    /* deterministic reduction to per-Gaussian screen-space gradients */
-    double *gs = (double *)calloc((size_t)(P > 0 ? P : 1) * 10, sizeof(double));
-    for (int64_t j = 0; j < D; j++) {
-        double *d = gs + (size_t)c->vals[j] * 10;
-        const double *s = part + (size_t)j * 10;
-        for (int k = 0; k < 10; k++) d[k] += s[k];
+    /* deterministic reduction to per-Gaussian screen-space gradients: every thread owns a contiguous range of Gaussian
+     * ids, scans the whole sorted list and adds the instances of ITS Gaussians in list order -- the same order of additions
+     * per Gaussian as a serial pass, for any thread count */
+    double *gs = (double *)malloc((size_t)(P > 0 ? P : 1) * 10 * sizeof(double));
+#pragma omp parallel
+    {
+#ifdef _OPENMP
+        const int nt = omp_get_num_threads(), it = omp_get_thread_num();
+#else
+        const int nt = 1, it = 0;
+#endif
+        const uint32_t lo = (uint32_t)((uint64_t)P * it / nt), hi = (uint32_t)((uint64_t)P * (it + 1) / nt);
+        if (hi > lo) memset(gs + (size_t)lo * 10, 0, sizeof(double) * 10 * (size_t)(hi - lo));
+        for (int64_t j = 0; j < D; j++) {
+            const uint32_t g = c->vals[j];
+            if (g < lo || g >= hi) continue;
+            double *d = gs + (size_t)g * 10;
+            const double *s = part + (size_t)j * 10;
+            for (int k = 0; k < 10; k++) d[k] += s[k];
+        }
     }
     free(part);
 
