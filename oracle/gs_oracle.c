@@ -307,13 +307,9 @@ static void radix_sort(uint64_t *k, uint64_t *kt, uint32_t *v, uint32_t *vt, int
     uint64_t *ki = k, *ko = kt;
     uint32_t *vi = v, *vo = vt;
     for (int shift = 0; shift < nbits; shift += 8) {
-#pragma omp parallel num_threads(nt)
-        {
-#ifdef _OPENMP
-            const int t = omp_get_thread_num();
-#else
-            const int t = 0;
-#endif
+        /* a loop over the nt CHUNKS (not over thread ids): every chunk is processed whatever team size the runtime grants */
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+        for (int t = 0; t < nt; t++) {
             const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
             int64_t *h = cnt + 256 * (size_t)t;
             memset(h, 0, sizeof(int64_t) * 256);
@@ -326,13 +322,8 @@ static void radix_sort(uint64_t *k, uint64_t *kt, uint32_t *v, uint32_t *vt, int
                 cnt[256 * (size_t)t + d] = run;
                 run += c0;
             }
-#pragma omp parallel num_threads(nt)
-        {
-#ifdef _OPENMP
-            const int t = omp_get_thread_num();
-#else
-            const int t = 0;
-#endif
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+        for (int t = 0; t < nt; t++) {
             const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
             int64_t *h = cnt + 256 * (size_t)t;
             for (int64_t i = lo; i < hi; i++) {
