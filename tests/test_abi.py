@@ -163,3 +163,26 @@ def test_state_pool_parks_and_reuses_buffer_sets():
     assert pool.take("ctx") is bufs
     e = R.InstanceLimitError(1 << 32)
     assert e.count == 1 << 32 and "4294967296" in str(e) and isinstance(e, RuntimeError)
+
+
+def test_view_batch_sink_hands_each_view_its_gradient_row():
+    """renderer._StackSinks (pure autograd, no GPU): the [V,P,3] batch sink aliases V leaf tensors; backward fills each
+    leaf's .grad with its row, which is what the reference's hook sums (GaussianDreamer.py:385-387)."""
+    import torch
+    from humangaussian_b200.renderer import _StackSinks
+    V, P = 4, 6
+    base = torch.zeros(V, P, 3)
+    sinks = [t.requires_grad_(True) for t in base.unbind(0)]
+    m = _StackSinks.apply(base, *sinks)
+    m.retain_grad()
+    assert m.shape == (V, P, 3) and m.data_ptr() == base.data_ptr()      # forward copies nothing
+    w = torch.arange(V * P * 3, dtype=torch.float32).reshape(V, P, 3)
+    (m * w).sum().backward()
+    for v in range(V):
+        assert sinks[v].is_leaf and torch.equal(sinks[v].grad, w[v])
+    assert torch.equal(m.grad, w)
+    # the hook body of the reference, verbatim
+    viewspace_point_tensor_grad = torch.zeros_like(sinks[0])
+    for idx in range(len(sinks)):
+        viewspace_point_tensor_grad = viewspace_point_tensor_grad + sinks[idx].grad
+    assert torch.equal(viewspace_point_tensor_grad, w.sum(0))
